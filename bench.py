@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- MLPG frames/s on BASELINE.json configs[1] (batched MLPG, 256 utterances T~600,
+D=187 Merlin layout, 3 windows, per-frame diagonal variances, float32 in / float64 arithmetic).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path (banded W^T S^-1 W assemble + factor + solve for every static
+dimension of every utterance) over one batch of synthetic input.  Prints ONE JSON line (rank 0).
+
+  value     : whole-job frames/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e       : the same metric through the public host-buffer API (nnmnkwii_b200.paramgen.mlpg_batch
+              on pinned NumPy arrays -> C ABI nnk_mlpg_batch_host): H2D + solve + D2H every step
+  roofline  : algorithmic bytes of the dominant kernel / its CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline : the reference's own CPU path (oracle/_ref = unmodified nnmnkwii, per utterance and per
+              stream paramgen.mlpg as in its gallery notebooks) on this box's host cores
+  --impl reference : times that CPU path only (rank 0), same metric/config/unit.
+
+Multi-GPU (torchrun, one rank per GPU): every rank solves its own 256-utterance slice (weak scaling,
+no data-path collective); one NCCL all_gather of the trajectories at the end, inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_UTT = 256
+T_LO, T_HI = 540, 660
+D_IN, D_OUT = 187, 63
+ALGO_BYTES_PER_FRAME = 1744  # 186 cols mean + 186 cols variance in, 62 out, vuv copy 4+4 (f32)
+WINDOWS = [(0, 0, np.array([1.0])), (1, 1, np.array([-0.5, 0.0, 0.5])), (1, 1, np.array([1.0, -2.0, 1.0]))]
+METRIC = "mlpg_frames_per_sec"
+UNIT = "frames/s"
+
+
+def make_batch(rank):
+    rng = np.random.default_rng(1234 + rank)
+    lens = rng.integers(T_LO, T_HI + 1, size=N_UTT)
+    n = int(lens.sum())
+    means = rng.random((n, D_IN), dtype=np.float32)
+    variances = rng.random((n, D_IN), dtype=np.float32) + np.float32(0.1)
+    return lens, means, variances
+
+
+def config(n_gpus):
+    return {
+        "workload": "configs[1]: batched paramgen.mlpg, %d utterances/GPU, T~U{%d..%d}, D=187 (mgc 180 + lf0 3 + vuv 1 "
+                    "copied + bap 3), 3 windows, per-frame diagonal variances, float32 I/O" % (N_UTT, T_LO, T_HI),
+        "utterances_per_gpu": N_UTT, "static_dims": 62, "windows": 3,
+        "sharding": "utterance-sharded, %d rank(s), one final NCCL all_gather" % n_gpus,
+        "cache": "inputs (230 MB) + factor scratch (236 MB) per step exceed the 126 MB L2; no explicit flush",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference arm
+# ---------------------------------------------------------------------------------------------------
+def _ref_worker_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    global _BATCH
+    lens, m, v = make_batch(0)  # workers own the data: no pickling of 230 MB through pipes per step
+    _BATCH = (np.concatenate([[0], np.cumsum(lens)]), m, v)
+    import warnings
+    warnings.simplefilter("ignore")
+    import oracle
+    global _G
+    if oracle.reference_available():
+        oracle.import_reference()
+        from nnmnkwii import paramgen as G_
+        _G = G_.mlpg
+    else:
+        _G = oracle.mlpg
+
+
+def _ref_one(u):
+    off, m_all, v_all = _BATCH
+    m, v = m_all[off[u]:off[u + 1]], v_all[off[u]:off[u + 1]]
+    # the gallery-notebook pattern: per utterance, one paramgen.mlpg call per stream; vuv copied
+    out = np.empty((m.shape[0], D_OUT), dtype=m.dtype)
+    out[:, 0:60] = _G(m[:, 0:180], v[:, 0:180], WINDOWS)
+    out[:, 60:61] = _G(m[:, 180:183], v[:, 180:183], WINDOWS)
+    out[:, 61] = m[:, 183]
+    out[:, 62:63] = _G(m[:, 184:187], v[:, 184:187], WINDOWS)
+    return out.shape[0]
+
+
+def cpu_reference(lens, means, variances, n_sample, repeats, cores):
+    """frames/s of the reference CPU path on `n_sample` utterances of the workload, `cores` processes."""
+    import multiprocessing as mp
+    import oracle
+    kind = "reference" if oracle.reference_available() else "port"
+    off = np.concatenate([[0], np.cumsum(lens)])
+    items = list(range(n_sample))
+    frames = int(off[n_sample])
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores, initializer=_ref_worker_init) as pool:
+        pool.map(_ref_one, items[: max(cores, 8)])  # warm-up (imports, page-in)
+        best = float("inf")
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_ref_one, items, chunksize=max(1, n_sample // (cores * 4)))
+            dt = time.perf_counter() - t0
+            times.append(dt)
+            best = min(best, dt)
+    return {"value": frames / best, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d of %d utterances (%d frames), per-utterance per-stream paramgen.mlpg, %d processes, best of %d"
+                      % (n_sample, len(lens), frames, cores, repeats)}, times, frames
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lens, means, variances = make_batch(0)
+    cores = os.cpu_count() or 1
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # each step = one bounded sample of the workload (whole batch is ~1.5 CPU-seconds on one core)
+    n_sample = N_UTT
+    base, times, frames = cpu_reference(lens, means, variances, n_sample, steps + warm, cores)
+    timed = times[warm:] if len(times) > warm else times
+    total = sum(timed)
+    val = frames * len(timed) / total
+    base["value"] = val
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
+        "warmup": warm, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args.gpus),
+        "cpu_baseline": base,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smmax, reasons, busy = [], [], set(), []
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx, util = float(f[1]), float(f[2]), float(f[4])
+            except ValueError:
+                continue
+            sm.append(clk); smmax.append(mx)
+            if util > 0:
+                busy.append(clk)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        use = busy or sm
+        return {"sm_mhz": statistics.median(use) if use else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(busy)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    lens, means, variances = make_batch(rank)
+
+    # CPU baseline first (rank 0, before CUDA is touched in this process; spawn-based pool)
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cpu_base, _, _ = cpu_reference(lens, means, variances, N_UTT, 3, cores)
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from nnmnkwii_b200 import _device as dev
+    from nnmnkwii_b200 import _lib
+    from nnmnkwii_b200 import paramgen as G
+
+    layout = G.merlin_layout()
+    n_rows = int(lens.sum())
+    off_np = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    wc = _lib.make_windows(WINDOWS)
+
+    # ---- device-resident arm --------------------------------------------------------------------
+    d_m = torch.from_numpy(means).to(device)
+    d_v = torch.from_numpy(variances).to(device)
+    d_out = torch.zeros((n_rows, D_OUT), dtype=torch.float32, device=device)
+    d_off = torch.from_numpy(off_np).to(device)
+    d_order = torch.from_numpy(np.argsort(-lens, kind="stable").astype(np.int32)).to(device)
+    d_chains = dev.chains_on_device(layout.chains, device)
+    max_T = int(lens.max())
+
+    def step():
+        return dev.run_mlpg("fwd", means=d_m, variances=d_v, rhs=None, out=d_out, offsets=d_off, lengths=None,
+                            order=d_order, chains=d_chains, n_chain=layout.n_chain, max_T=max_T, windows_c=wc,
+                            in_ld=D_IN, var_ld=D_IN, go_ld=0, out_ld=D_OUT, dtype_code=_lib.NNK_F32, go_f64=0,
+                            n_utt=N_UTT, device=device, check=False)
+
+    gathered = torch.empty((world, T_HI * N_UTT, D_OUT), dtype=torch.float32, device=device) if world > 1 else None
+    pad_out = torch.zeros((T_HI * N_UTT, D_OUT), dtype=torch.float32, device=device) if world > 1 else None
+
+    for _ in range(max(3, args.warmup)):
+        status = step()
+    torch.cuda.synchronize()
+    dev.raise_if_failed(status)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n0 = _lib.launch_count()
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        kev[i][0].record()
+        step()
+        kev[i][1].record()
+    ag_ms = 0.0
+    if world > 1:  # the one collective: all_gather of the trajectories at the end of the job
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        pad_out[:n_rows].copy_(d_out)
+        dist.all_gather_into_tensor(gathered.view(-1), pad_out.view(-1))
+        a1.record()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    total_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        ag_ms = a0.elapsed_time(a1)
+    kernel_ms = [a.elapsed_time(b) for a, b in kev]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    frames_t = torch.tensor([float(n_rows)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(frames_t, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    frames_all = float(frames_t.item())
+    value = frames_all * args.steps / (total_ms * 1e-3)
+
+    # parity spot check of what was just timed (utterance 0, mgc stream) against the oracle
+    parity = None
+    if rank == 0:
+        import oracle
+        a, b = int(off_np[0]), int(off_np[1])
+        ref = oracle.mlpg(means[a:b, :180], variances[a:b, :180], WINDOWS)
+        got = d_out[a:b, :60].cpu().numpy()
+        parity = float(np.abs(got - ref).max() / np.abs(ref).max())
+
+    # ---- end-to-end arm: public API on pinned host buffers ------------------------------------------
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    pm = torch.from_numpy(means).pin_memory()
+    pv = torch.from_numpy(variances).pin_memory()
+    hm, hv = pm.numpy(), pv.numpy()
+    for _ in range(2):
+        y = G.mlpg_batch(hm, hv, WINDOWS, lengths=lens, layout=layout)
+    barrier()
+    n1 = _lib.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        y = G.mlpg_batch(hm, hv, WINDOWS, lengths=lens, layout=layout)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    launches += _lib.launch_count() - n1
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = frames_all * e2e_steps / float(te.item())
+    if rank == 0:
+        assert np.array_equal(y[: int(off_np[1])], d_out[: int(off_np[1])].cpu().numpy()), "e2e and device paths disagree"
+
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    k_ms = statistics.mean(kernel_ms)
+    achieved = ALGO_BYTES_PER_FRAME * n_rows / (k_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config(world),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(means.nbytes + variances.nbytes),
+                "d2h_bytes_per_step": int(n_rows * D_OUT * 4), "steps": e2e_steps,
+                "api": "nnmnkwii_b200.paramgen.mlpg_batch(numpy pinned) -> nnk_mlpg_batch_host"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "mlpg_kernel<float,3,1,1,FWD>",
+                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * n_rows},
+        "cpu_baseline": cpu_base,
+        "clocks": clocks,
+        "allgather_ms": ag_ms,
+        "parity_max_rel_err_vs_oracle": parity,
+        "frames_per_step_per_gpu": n_rows,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

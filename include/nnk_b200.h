@@ -1,0 +1,162 @@
+/*
+ * nnk_b200.h -- C ABI of libnnk_b200.so: the B200 (sm_100a) implementation of nnmnkwii's two
+ * numeric hot paths, MLPG trajectory smoothing and DTW alignment.
+ *
+ * The reference (r9y9/nnmnkwii v0.1.3) has no FFI/plugin registry: its boundary is a set of Python
+ * callables backed by Cython extensions.  Each entry point below names the reference interface
+ * (file:line under /root/reference) whose arithmetic it replaces; INTEGRATION.md shows the ctypes
+ * stub a reference maintainer would add at each of those call sites.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - "device" pointers are CUDA device memory owned by the caller; "host" pointers are ordinary
+ *     (ideally pinned) host memory.  All matrices are row-major.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Device entry points are asynchronous: they enqueue work on `stream` and return.  Numerical
+ *     failures (non-positive pivot) are written to a caller-provided device status record that the
+ *     host inspects after synchronising (nnk_status_t).  Host entry points synchronise internally.
+ *   - Return value: NNK_OK or a negative NNK_ERR_* (argument / CUDA errors; nnk_last_error() has text).
+ *   - There is no CPU fallback anywhere in this library.
+ */
+#ifndef NNK_B200_H
+#define NNK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNK_ABI_VERSION 1
+
+#define NNK_OK 0
+#define NNK_ERR_ARG -1          /* bad argument                                               */
+#define NNK_ERR_UNSUPPORTED -2  /* window set larger than NNK_MAX_WIN / NNK_MAX_HALF           */
+#define NNK_ERR_CUDA -3         /* CUDA runtime error                                          */
+#define NNK_ERR_WORKSPACE -4    /* workspace too small (see *_workspace_bytes)                 */
+#define NNK_ERR_NOT_PD -5       /* host entry points only: non-positive pivot (see status)     */
+
+#define NNK_F32 0
+#define NNK_F64 1
+
+#define NNK_MAX_WIN 4  /* windows per stream (static, delta, delta-delta, +1)                  */
+#define NNK_MAX_HALF 4 /* max(l, u) of any window                                              */
+#define NNK_MAX_TAPS (2 * NNK_MAX_HALF + 1)
+
+/* Windows = the reference's list of (l, u, win_coeff) triples (paramgen/_mlpg.py:16-20).
+ * coef[w][0 .. l[w]+u[w]] holds win_coeff of window w.                                        */
+typedef struct nnk_windows {
+  int32_t nw;
+  int32_t l[NNK_MAX_WIN];
+  int32_t u[NNK_MAX_WIN];
+  double coef[NNK_MAX_WIN][NNK_MAX_TAPS];
+} nnk_windows_t;
+
+/* Failure record.  On the device it is ONE zero-initialised uint64 word (`status_word`) that the
+ * kernels update atomically so that the lexicographically first failure (utterance, chain, frame)
+ * wins -- the order in which the reference's Python loops would have raised.  The host decodes
+ * it with nnk_status_decode().
+ *   code 0 = ok, 1 = non-positive pivot (reference: scipy.linalg.LinAlgError
+ *   "%d-th leading minor not positive definite", _bandmat/linalg.pyx:79-82)                    */
+typedef struct nnk_status {
+  int32_t code;
+  int32_t utt;   /* utterance index                                                           */
+  int32_t chain; /* chain index (static dimension within the layout)                          */
+  int32_t frame; /* 1-based frame of the pivot, as in the reference's message                 */
+} nnk_status_t;
+
+/* One "chain" = one static dimension of one stream = one banded T x T solve.
+ * A (T, D) frame matrix in Merlin layout holds several streams side by side (e.g. mgc 180 = 3 x 60,
+ * lf0 3, vuv 1, bap 3); chain c reads window w of its stream at column in_col + w * win_stride and
+ * writes its trajectory to column out_col.  flags & 1 = pass-through (copy in_col -> out_col, no
+ * smoothing: the vuv column of the gallery notebooks).                                          */
+typedef struct nnk_chain {
+  int32_t in_col;
+  int32_t win_stride;
+  int32_t out_col;
+  int32_t flags;
+} nnk_chain_t;
+
+/* Batched MLPG over a flat (n_rows, ld) frame matrix holding n_utt utterances back to back.    */
+typedef struct nnk_mlpg_args {
+  const void* means;          /* device (n_rows, in_ld)   dtype                                */
+  const void* vars;           /* device (n_rows, var_ld) per-frame variances, or (>= D,) global
+                                 variances when var_ld == 0 (paramgen/_mlpg.py:169-170)        */
+  const void* grad_out;       /* device (n_rows, go_ld): nnk_mlpg_grad: backpropagated gradient;
+                                 nnk_mlpg_solve: right-hand sides.  Chain c reads column c.
+                                 float32, or float64 when go_f64 != 0                          */
+  void* out;                  /* device: fwd (n_rows, out_ld) dtype ; grad (n_rows, out_ld) f32 */
+  int32_t dtype;              /* NNK_F32 / NNK_F64 of means, vars (and out for fwd)            */
+  int32_t n_utt;
+  int64_t in_ld, var_ld, go_ld, out_ld; /* row strides in elements                            */
+  const int64_t* utt_off;     /* device (n_utt + 1) row offsets                                */
+  const int32_t* utt_len;     /* device (n_utt) frame counts, or NULL => utt_off[u+1]-utt_off[u];
+                                 lets zero-padded (B, Tmax, D) batches be used in place        */
+  const int32_t* order;       /* device (n_utt) processing order (e.g. longest first) or NULL  */
+  const nnk_chain_t* chains;  /* device (n_chain)                                              */
+  int32_t n_chain;
+  int32_t max_T;              /* max utterance length (host knows it; sizes the workspace)     */
+  int32_t go_f64;             /* grad_out / rhs element type: 0 = float32, 1 = float64         */
+  nnk_windows_t win;
+  void* workspace;            /* device scratch, >= nnk_mlpg_workspace_bytes()                 */
+  size_t workspace_bytes;
+  uint64_t* status_word;      /* device; must be zeroed by the caller before the first launch  */
+} nnk_mlpg_args_t;
+
+void nnk_status_decode(uint64_t status_word, nnk_status_t* out);
+
+/* Replaces paramgen.mlpg (paramgen/_mlpg.py:92-199: build_poe :53-89, bla.solveh
+ * _bandmat/linalg.pyx:290-304) for a whole batch: out[:, chain.out_col] = P^{-1} b per chain.   */
+int nnk_mlpg_fwd(const nnk_mlpg_args_t* args, void* stream);
+
+/* Replaces paramgen.mlpg_grad (paramgen/_mlpg.py:202-281) in closed form:
+ * out[:, in_col + w*win_stride] = tau_w * (W_w P^{-1} grad_out[:, chain]); out is float32.      */
+int nnk_mlpg_grad(const nnk_mlpg_args_t* args, void* stream);
+
+/* General banded solve with the same P: out[:, chain.out_col] = P^{-1} rhs[:, chain] (dtype of
+ * `out` = args->dtype).  Used to build unit_variance_mlpg_matrix (paramgen/_mlpg.py:297-373):
+ * R = P^{-1} Wtilde^T with unit variances, one chain per column of Wtilde^T.                    */
+int nnk_mlpg_solve(const nnk_mlpg_args_t* args, void* stream);
+
+/* Scratch needed by the calls above for `n_utt` utterances of at most max_T frames.         */
+size_t nnk_mlpg_workspace_bytes(int32_t n_utt, int32_t n_chain, int32_t max_T, const nnk_windows_t* win);
+
+/* Host-buffer convenience = what a cgo/ctypes binding of paramgen.mlpg would call: one utterance,
+ * one stream, host pointers (means (T, D), variances (T, D) or (D,), out (T, D / nw)), copies
+ * included, synchronous.  Returns NNK_ERR_NOT_PD with *bad_frame = 1-based frame on failure.    */
+int nnk_mlpg_host(const void* means, const void* vars, int32_t var_is_1d, int32_t dtype, int64_t T,
+                  int64_t D, const nnk_windows_t* win, void* out, int32_t* bad_frame);
+
+/* Host-buffer batched MLPG: flat (n_rows, D) host matrices, chains/offsets on the host.  H2D and
+ * D2H copies run chunked on two streams so they overlap the solve.  This is the end-to-end path
+ * bench.py times as `e2e`.                                                                      */
+int nnk_mlpg_batch_host(const void* means, const void* vars, int32_t var_is_1d, int32_t dtype,
+                        int64_t n_rows, int64_t D, int64_t D_out, const int64_t* utt_off, int32_t n_utt,
+                        const nnk_chain_t* chains, int32_t n_chain, const nnk_windows_t* win, void* out,
+                        nnk_status_t* status);
+
+/* ---- UnitVarianceMLPG (autograd/_impl/mlpg.py:70-172) ------------------------------------------
+ * R (T, nw*T) row-major device matrix (float32, or float64 when dtype == NNK_F64) as produced by
+ * unit_variance_mlpg_matrix (paramgen/_mlpg.py:297-373).
+ * 1. nnk_uv_band_profile: profile[dist] = max |R[t, w*T+s]| over |t-s| == dist (T floats); the
+ *    host picks the half-width K from it.
+ * 2. nnk_uv_band_extract: Rb, RbT (T, nw, 2K+1) band tables (same dtype as R).
+ * 3. nnk_uv_apply: backward == 0: y (B, T, sd) = R x   replacing torch.matmul(R, reshaped_means)
+ *    (mlpg.py:138); backward != 0: y = R^T x replacing torch.matmul(R.transpose(0,1), grad_output)
+ *    (mlpg.py:158).  The nw-window side is (B, T, nw*sd) when reshaped == 0 or (B, nw*T, sd)
+ *    when reshaped != 0 (mlpg.py:124-136, :160-167); the other side is (B, T, sd).               */
+int nnk_uv_band_profile(const void* R, int32_t dtype, int32_t T, int32_t nw, float* profile, void* stream);
+int nnk_uv_band_extract(const void* R, int32_t dtype, int32_t T, int32_t nw, int32_t K, void* Rb, void* RbT, void* stream);
+int nnk_uv_apply(const void* table, const void* x, void* y, int32_t dtype, int32_t B, int32_t T, int32_t sd,
+                 int32_t nw, int32_t K, int32_t backward, int32_t reshaped, void* stream);
+
+const char* nnk_last_error(void);
+int nnk_abi_version(void);
+/* Number of kernel launches this library has issued since load (bench.py's gpu_launches).       */
+int64_t nnk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNK_B200_H */

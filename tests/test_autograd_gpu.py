@@ -1,0 +1,168 @@
+"""GPU: autograd.MLPG / UnitVarianceMLPG, mirroring the reference's tests/test_autograd.py
+(gradcheck eps=1e-3 atol=1e-3 on float32, minibatch == per-item, variance expansion) plus parity
+with the golden fwd/bwd vectors produced by the reference's own autograd Functions."""
+import numpy as np
+import pytest
+import torch
+from torch.autograd import gradcheck
+
+import oracle
+from conftest import rel_err, windows_set
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from nnmnkwii_b200 import autograd as AF
+    from nnmnkwii_b200 import paramgen as G
+    return AF, G
+
+
+def test_golden_unit_variance_fwd_bwd(golden):
+    AF, G = _mods()
+    ws = windows_set()[2]
+    mu = torch.from_numpy(golden["uv_means"]).requires_grad_(True)
+    R = torch.from_numpy(G.unit_variance_mlpg_matrix(ws, mu.shape[1]))
+    y = AF.unit_variance_mlpg(R, mu)
+    assert rel_err(y.detach().numpy(), golden["uv_y"]) < 1e-5
+    (y * torch.from_numpy(golden["uv_wgt"])).sum().backward()
+    assert rel_err(mu.grad.numpy(), golden["uv_grad"]) < 1e-5
+    # CUDA tensors stay on the device
+    muc = torch.from_numpy(golden["uv_means"]).cuda().requires_grad_(True)
+    yc = AF.unit_variance_mlpg(R.cuda(), muc)
+    assert yc.is_cuda and rel_err(yc.detach().cpu().numpy(), golden["uv_y"]) < 1e-5
+
+
+def test_golden_mlpg_fwd_bwd(golden):
+    AF, G = _mods()
+    ws = windows_set()[2]
+    mu = torch.from_numpy(golden["ag_means"]).requires_grad_(True)
+    y = AF.mlpg(mu, torch.from_numpy(golden["ag_vars"]), ws)
+    assert y.dtype == torch.float32 and rel_err(y.detach().numpy(), golden["ag_y"]) < 1e-6
+    (y * torch.from_numpy(golden["ag_wgt"])).sum().backward()
+    assert rel_err(mu.grad.numpy(), golden["ag_grad"]) < 2e-6
+
+
+def test_functional_mlpg_equivalences():
+    """reference tests/test_autograd.py:39-72"""
+    AF, G = _mods()
+    static_dim, T = 2, 10
+    for windows in windows_set():
+        torch.manual_seed(1234)
+        means = torch.rand(T, static_dim * len(windows))
+        variances = torch.ones(static_dim * len(windows))
+        y = G.mlpg(means.numpy(), variances.numpy(), windows)
+        y = torch.from_numpy(y).clone()
+        means = means.clone().requires_grad_(True)
+        y_hat = AF.mlpg(means, variances, windows)
+        assert np.allclose(y.numpy(), y_hat.detach().numpy(), atol=1e-6)
+        torch.nn.MSELoss()(y_hat, y).backward()
+        R = torch.from_numpy(G.unit_variance_mlpg_matrix(windows, T))
+        y_hat = AF.unit_variance_mlpg(R, means)
+        assert np.allclose(y.numpy(), y_hat.detach().numpy(), atol=1e-5)
+        torch.nn.MSELoss()(y_hat, y).backward()
+        y_hat = AF.unit_variance_mlpg(R, means.view(1, -1, means.size(-1)))
+        assert np.allclose(y.numpy(), y_hat.detach().numpy()[0], atol=1e-5)
+
+
+def test_unit_variance_mlpg_gradcheck():
+    """reference tests/test_autograd.py:75-113"""
+    AF, G = _mods()
+    static_dim, T = 2, 10
+    for windows in windows_set():
+        torch.manual_seed(1234)
+        means = torch.rand(T, static_dim * len(windows), requires_grad=True)
+        variances = torch.ones(static_dim * len(windows)).expand(T, static_dim * len(windows))
+        y1 = AF.MLPG.apply(means, variances, windows)
+        R = torch.from_numpy(G.unit_variance_mlpg_matrix(windows, T))
+        y2 = AF.UnitVarianceMLPG.apply(means, R)
+        assert np.allclose(y1.detach().numpy(), y2.detach().numpy(), atol=1e-5)
+        assert gradcheck(AF.UnitVarianceMLPG.apply, (means, R), eps=1e-3, atol=1e-3)
+        reshaped = torch.from_numpy(G.reshape_means(means.detach().numpy(), static_dim)).requires_grad_(True)
+        assert gradcheck(AF.UnitVarianceMLPG.apply, (reshaped, R), eps=1e-3, atol=1e-3)
+
+
+def test_minibatch_unit_variance_mlpg():
+    """reference tests/test_autograd.py:116-177: 3-D batch == per item; stride-0 expanded batch."""
+    AF, G = _mods()
+    static_dim, T, batch_size = 2, 5, 3
+    for windows in windows_set():
+        torch.manual_seed(0)
+        means = torch.rand(T, static_dim * len(windows), requires_grad=True)
+        means_expanded = means.expand(batch_size, means.shape[0], means.shape[1])
+        reshaped = torch.from_numpy(G.reshape_means(means.detach().numpy(), static_dim)).requires_grad_(True)
+        reshaped_expanded = reshaped.expand(batch_size, reshaped.shape[0], reshaped.shape[1])
+        R = torch.from_numpy(G.unit_variance_mlpg_matrix(windows, T))
+        y = AF.unit_variance_mlpg(R, means)
+        y_b = AF.unit_variance_mlpg(R, means_expanded)
+        y_rb = AF.unit_variance_mlpg(R, reshaped_expanded)
+        assert y_b.shape == (batch_size, T, static_dim)
+        for i in range(batch_size):
+            assert np.allclose(y.detach().numpy(), y_b[i].detach().numpy(), atol=1e-6)
+            assert np.allclose(y.detach().numpy(), y_rb[i].detach().numpy(), atol=1e-6)
+        # gradients
+        nlf = torch.nn.MSELoss()
+        tgt = torch.rand(T, static_dim)
+        means.grad = None
+        nlf(AF.unit_variance_mlpg(R, means), tgt).backward()
+        g1 = means.grad.clone()
+        mb = means.detach().clone().expand(batch_size, T, means.shape[1]).contiguous().requires_grad_(True)
+        nlf(AF.unit_variance_mlpg(R, mb), tgt.expand(batch_size, T, static_dim)).backward()
+        for i in range(batch_size):
+            assert np.allclose(g1.numpy(), mb.grad[i].numpy() * batch_size, atol=1e-6)
+
+
+def test_mlpg_gradcheck():
+    """reference tests/test_autograd.py:180-204 (stride-0 expanded / random variances)"""
+    AF, G = _mods()
+    static_dim, T = 2, 10
+    for windows in windows_set():
+        torch.manual_seed(1234)
+        means = torch.rand(T, static_dim * len(windows), requires_grad=True)
+        variances = torch.ones(static_dim * len(windows)).expand(T, static_dim * len(windows))
+        assert gradcheck(AF.MLPG.apply, (means, variances, windows), eps=1e-3, atol=1e-3)
+        variances = torch.rand(static_dim * len(windows)).expand(T, static_dim * len(windows))
+        assert gradcheck(AF.MLPG.apply, (means, variances, windows), eps=1e-3, atol=1e-3)
+
+
+def test_mlpg_variance_expand():
+    """reference tests/test_autograd.py:207-218"""
+    AF, G = _mods()
+    static_dim, T = 2, 10
+    for windows in windows_set():
+        torch.manual_seed(1234)
+        means = torch.rand(T, static_dim * len(windows), requires_grad=True)
+        variances = torch.rand(static_dim * len(windows))
+        y1 = AF.mlpg(means, variances, windows)
+        y2 = AF.mlpg(means, variances.expand(T, static_dim * len(windows)), windows)
+        assert np.allclose(y1.detach().numpy(), y2.detach().numpy())
+
+
+def test_cfg3_full_size_unit_variance():
+    """BASELINE.json configs[2]: batch=64, T=1000, static_dim=60, fwd + loss.backward() on the GPU.
+    Checked against the float64 dense product with the SAME R on a slice, and by the adjoint
+    identity <R x, o> == <x, R^T o> on everything."""
+    AF, G = _mods()
+    ws = windows_set()[2]
+    T, sd, B = 1000, 60, 64
+    R = torch.from_numpy(G.unit_variance_mlpg_matrix(ws, T)).cuda()
+    assert np.abs(R[:, :].cpu().numpy()[::97] - oracle.unit_variance_mlpg_matrix(ws, T)[::97]).max() < 2e-7
+    g = torch.Generator(device="cuda").manual_seed(1)
+    mu = torch.randn(B, T, 3 * sd, device="cuda", generator=g).requires_grad_(True)
+    y = AF.unit_variance_mlpg(R, mu)
+    assert y.shape == (B, T, sd)
+    loss = y.pow(2).mean()
+    loss.backward()
+    # dense float64 check on 2 batch items
+    Rd = R.double()
+    for b in (0, 63):
+        xr = mu[b].detach().double().view(T, 3, sd).transpose(0, 1).reshape(3 * T, sd)
+        yref = Rd @ xr
+        assert rel_err(y[b].detach().cpu().numpy(), yref.cpu().numpy()) < 1e-5
+        gref = (Rd.t() @ (2.0 * yref / (B * T * sd))).view(3, T, sd).transpose(0, 1).reshape(T, 3 * sd)
+        assert rel_err(mu.grad[b].cpu().numpy(), gref.cpu().numpy()) < 1e-5
+    o = torch.randn(B, T, sd, device="cuda", generator=g)
+    lhs = (y.detach().double() * o.double()).sum()
+    (gx,) = torch.autograd.grad(AF.unit_variance_mlpg(R, mu), mu, o)
+    rhs = (mu.detach().double() * gx.double()).sum()
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5
