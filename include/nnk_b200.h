@@ -151,6 +151,48 @@ int nnk_uv_band_extract(const void* R, int32_t dtype, int32_t T, int32_t nw, int
 int nnk_uv_apply(const void* table, const void* x, void* y, int32_t dtype, int32_t B, int32_t T, int32_t sd,
                  int32_t nw, int32_t K, int32_t backward, int32_t reshaped, void* stream);
 
+/* ---- DTW alignment (preprocessing/alignment.py:9-190) ------------------------------------------
+ * Batched replacement of `dist, path = fastdtw(x, y, radius=self.radius, dist=self.dist)`
+ * (alignment.py:50, :138; third-party slaypni/fastdtw, unpinned in setup.py:139 -- see DESIGN.md
+ * "parity unpinned").  One CTA per pair; radius < 0 = exact DTW (full anti-diagonal wavefront),
+ * radius >= 1 = FastDTW with that radius.  cost_kind 0 = default lambda x, y: norm(x - y)
+ * (alignment.py:35), 1 = metrics.melcd (metrics/__init__.py:27-57).  Arithmetic is float64.     */
+typedef struct nnk_dtw_args {
+  const void* X;              /* device (n_pairs, .., D): pair p, frame t at X + p*x_pair_stride + t*x_ld */
+  const void* Y;
+  int32_t dtype;              /* NNK_F32 / NNK_F64 of X and Y                                   */
+  int32_t n_pairs;
+  int64_t x_pair_stride, y_pair_stride; /* elements                                           */
+  int32_t x_ld, y_ld, D;
+  const int32_t* len_x;       /* device (n_pairs): frames kept by trim_zeros_frames (alignment.py:49) */
+  const int32_t* len_y;
+  const int32_t* order;       /* device (n_pairs) processing order or NULL                      */
+  int32_t cost_kind;
+  int32_t radius;
+  int32_t* path_i;            /* device (n_pairs, path_ld): pathx of alignment.py:52             */
+  int32_t* path_j;            /* device (n_pairs, path_ld): pathy                                */
+  int32_t path_ld;            /* >= max_tx + max_ty - 1                                         */
+  int32_t* path_len;          /* device (n_pairs)                                               */
+  double* dist;               /* device (n_pairs): accumulated cost D[Tx-1, Ty-1]               */
+  int64_t* cells;             /* device (n_pairs) DP cells evaluated, or NULL                   */
+  int32_t max_tx, max_ty;
+  void* workspace;
+  size_t workspace_bytes;     /* >= nnk_dtw_workspace_bytes()                                   */
+} nnk_dtw_args_t;
+
+int nnk_dtw_align(const nnk_dtw_args_t* args, void* stream);
+size_t nnk_dtw_workspace_bytes(int32_t n_pairs, int32_t max_tx, int32_t max_ty, int32_t D, int32_t radius);
+
+/* out[p, r, :] = X[p, path[p, r], :] for r < path_len[p], zero for r >= path_len[p]
+ * (x = x[pathx]; X_aligned[idx][:len(x)] = x over a zero array: alignment.py:46-47, 52-54, 72-73)  */
+int nnk_gather_rows(const void* X, int32_t dtype, int64_t x_pair_stride, int32_t x_ld, const int32_t* path,
+                    int32_t path_ld, const int32_t* path_len, void* out, int64_t out_pair_stride, int32_t out_rows,
+                    int32_t D, int32_t n_pairs, void* stream);
+
+/* len[p] = len(trim_zeros_frames(X[p], eps, trim="b")) (preprocessing/generic.py:291-323)          */
+int nnk_trim_lengths(const void* X, int32_t dtype, int64_t pair_stride, int32_t ld, int32_t T, int32_t D, double eps,
+                     int32_t n_pairs, int32_t* len, void* stream);
+
 const char* nnk_last_error(void);
 int nnk_abi_version(void);
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches).       */

@@ -57,6 +57,35 @@ class NnkMlpgArgs(ctypes.Structure):
     ]
 
 
+class NnkDtwArgs(ctypes.Structure):
+    _fields_ = [
+        ("X", ctypes.c_void_p),
+        ("Y", ctypes.c_void_p),
+        ("dtype", ctypes.c_int32),
+        ("n_pairs", ctypes.c_int32),
+        ("x_pair_stride", ctypes.c_int64),
+        ("y_pair_stride", ctypes.c_int64),
+        ("x_ld", ctypes.c_int32),
+        ("y_ld", ctypes.c_int32),
+        ("D", ctypes.c_int32),
+        ("len_x", ctypes.c_void_p),
+        ("len_y", ctypes.c_void_p),
+        ("order", ctypes.c_void_p),
+        ("cost_kind", ctypes.c_int32),
+        ("radius", ctypes.c_int32),
+        ("path_i", ctypes.c_void_p),
+        ("path_j", ctypes.c_void_p),
+        ("path_ld", ctypes.c_int32),
+        ("path_len", ctypes.c_void_p),
+        ("dist", ctypes.c_void_p),
+        ("cells", ctypes.c_void_p),
+        ("max_tx", ctypes.c_int32),
+        ("max_ty", ctypes.c_int32),
+        ("workspace", ctypes.c_void_p),
+        ("workspace_bytes", ctypes.c_size_t),
+    ]
+
+
 CHAIN_DTYPE = np.dtype([("in_col", np.int32), ("win_stride", np.int32), ("out_col", np.int32), ("flags", np.int32)])
 
 # every symbol include/nnk_b200.h declares (tests check the library exports all of them)
@@ -64,6 +93,7 @@ EXPORTS = [
     "nnk_abi_version", "nnk_last_error", "nnk_launch_count", "nnk_status_decode",
     "nnk_mlpg_fwd", "nnk_mlpg_grad", "nnk_mlpg_solve", "nnk_mlpg_workspace_bytes", "nnk_mlpg_host", "nnk_mlpg_batch_host",
     "nnk_uv_band_profile", "nnk_uv_band_extract", "nnk_uv_apply",
+    "nnk_dtw_align", "nnk_dtw_workspace_bytes", "nnk_gather_rows", "nnk_trim_lengths",
 ]
 
 
@@ -104,6 +134,14 @@ def _load():
     L.nnk_uv_band_extract.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
     L.nnk_uv_apply.restype = ctypes.c_int
     L.nnk_uv_apply.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.nnk_dtw_align.restype = ctypes.c_int
+    L.nnk_dtw_align.argtypes = [ctypes.POINTER(NnkDtwArgs), vp]
+    L.nnk_dtw_workspace_bytes.restype = ctypes.c_size_t
+    L.nnk_dtw_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.nnk_gather_rows.restype = ctypes.c_int
+    L.nnk_gather_rows.argtypes = [vp, i32, i64, i32, vp, i32, vp, vp, i64, i32, i32, i32, vp]
+    L.nnk_trim_lengths.restype = ctypes.c_int
+    L.nnk_trim_lengths.argtypes = [vp, i32, i64, i32, i32, i32, ctypes.c_double, i32, vp, vp]
     return L
 
 

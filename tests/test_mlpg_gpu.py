@@ -95,11 +95,21 @@ def test_not_positive_definite_raises_like_reference():
     ws = windows_set()[2]
     rng = np.random.default_rng(3)
     m = rng.random((30, 6)); v = rng.random((30, 6)) + 0.1
-    v[:, 1] = -1.0  # negative static variance of dim 1 -> non-positive pivot at frame 1
-    with pytest.raises(np.linalg.LinAlgError, match="1-th leading minor not positive definite"):
-        G.mlpg(m, v, ws)
-    with pytest.raises(np.linalg.LinAlgError, match="1-th leading minor"):
+    v[:, 1] = -1.0  # negative static variance of dim 1 -> some pivot of chain 1 is not positive
+    with pytest.raises(np.linalg.LinAlgError) as e_ref:
         oracle.mlpg(m, v, ws)
+    ref_msg = str(e_ref.value)  # "<k>-th leading minor not positive definite" (linalg.pyx:79-82)
+    assert "leading minor not positive definite" in ref_msg
+    with pytest.raises(np.linalg.LinAlgError) as e_gpu:
+        G.mlpg(m, v, ws)
+    assert str(e_gpu.value).startswith(ref_msg), (str(e_gpu.value), ref_msg)  # same 1-based frame
+    # a failure in a later utterance / chain of a batch reports the first one in reference loop order
+    lens = [10, 12, 9]
+    mb = rng.random((31, 6)); vb = rng.random((31, 6)) + 0.1
+    vb[10:22, 0] = -1.0
+    vb[22:, 1] = -1.0
+    with pytest.raises(np.linalg.LinAlgError, match=r"utterance 1, chain 0"):
+        G.mlpg_batch(mb, vb, ws, lengths=lens)
 
 
 def test_mlpg_grad_vs_oracle():
