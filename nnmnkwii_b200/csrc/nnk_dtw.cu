@@ -50,40 +50,40 @@ struct DtwParams {
 
 // numpy DOUBLE_pairwise_sum order over a[k] = (x[k]-y[k])^2 without materialising a[]
 __device__ __forceinline__ double sq(const double* __restrict__ x, const double* __restrict__ y, int k) {
-  const double z = x[k] - y[k];
-  return z * z;
+  const double z = __dsub_rn(x[k], y[k]);
+  return __dmul_rn(z, z);  // never contracted into an FMA: numpy multiplies, then adds
 }
 __device__ __forceinline__ double strided8(const double* x, const double* y, int j, int n8) {
   double r = sq(x, y, j);
-  for (int i = 8; i < n8; i += 8) r += sq(x, y, i + j);
+  for (int i = 8; i < n8; i += 8) r = __dadd_rn(r, sq(x, y, i + j));
   return r;
 }
 __device__ double pairwise_block(const double* x, const double* y, int n) {  // n <= 128
   if (n < 8) {
     double res = -0.0;
-    for (int i = 0; i < n; ++i) res += sq(x, y, i);
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, sq(x, y, i));
     return res;
   }
   const int n8 = n - (n % 8);
-  const double s01 = strided8(x, y, 0, n8) + strided8(x, y, 1, n8);
-  const double s23 = strided8(x, y, 2, n8) + strided8(x, y, 3, n8);
-  const double s0123 = s01 + s23;
-  const double s45 = strided8(x, y, 4, n8) + strided8(x, y, 5, n8);
-  const double s67 = strided8(x, y, 6, n8) + strided8(x, y, 7, n8);
-  double res = s0123 + (s45 + s67);
-  for (int i = n8; i < n; ++i) res += sq(x, y, i);
+  const double s01 = __dadd_rn(strided8(x, y, 0, n8), strided8(x, y, 1, n8));
+  const double s23 = __dadd_rn(strided8(x, y, 2, n8), strided8(x, y, 3, n8));
+  const double s0123 = __dadd_rn(s01, s23);
+  const double s45 = __dadd_rn(strided8(x, y, 4, n8), strided8(x, y, 5, n8));
+  const double s67 = __dadd_rn(strided8(x, y, 6, n8), strided8(x, y, 7, n8));
+  double res = __dadd_rn(s0123, __dadd_rn(s45, s67));
+  for (int i = n8; i < n; ++i) res = __dadd_rn(res, sq(x, y, i));
   return res;
 }
 __device__ double pairwise_sumsq(const double* x, const double* y, int n) {
   if (n <= 128) return pairwise_block(x, y, n);
   int n2 = n / 2;
   n2 -= n2 % 8;
-  return pairwise_sumsq(x, y, n2) + pairwise_sumsq(x + n2, y + n2, n - n2);
+  return __dadd_rn(pairwise_sumsq(x, y, n2), pairwise_sumsq(x + n2, y + n2, n - n2));
 }
 
 __device__ __forceinline__ double local_cost(const double* x, const double* y, int D, int kind, double logdb) {
   const double r = sqrt(pairwise_sumsq(x, y, D));
-  return kind == 1 ? logdb * r : r;
+  return kind == 1 ? __dmul_rn(logdb, r) : r;
 }
 
 template <int BLOCK>

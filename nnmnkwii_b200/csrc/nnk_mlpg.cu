@@ -18,40 +18,12 @@
 // HBM.  L D L^T instead of the reference's L L^T: same pivots d[t] (so the same not-positive-
 // definite test, linalg.pyx:79), no sqrt on the loop-carried dependency chain, results agree to
 // rounding (1e-15 relative).
-#include "nnk_common.cuh"
+#include <stdlib.h>
+
+#include "nnk_mlpg.cuh"
+#include "nnk_mlpg_tma.cuh"
 
 namespace nnk {
-
-enum { MODE_FWD = 0, MODE_GRAD = 1, MODE_SOLVE = 2 };
-
-template <int NW, int L, int U>
-struct WinTab {
-  static constexpr int S = L + U;
-  static constexpr int NT = L + U + 1;
-  double c[NW][NT];         // c[w][L + k] = W_w[t, t + k]   (zero padded to the common (L, U))
-  double q[NW][S + 1][NT];  // q[w][m][i] = c[w][i] * c[w][i + m]
-  int nw;                   // real number of windows (<= NW)
-  int m_edge;               // max_w max(l_w, u_w): dynamic windows get zero precision at that many
-                            // edge frames (paramgen/_mlpg.py:177, 190-193)
-};
-
-template <typename Tin, int NW, int L, int U>
-struct MlpgParams {
-  const Tin* means;
-  const Tin* vars;
-  const void* go;
-  int go_f64;
-  void* out;
-  int64_t in_ld, var_ld, go_ld, out_ld;
-  const int64_t* utt_off;
-  const int32_t* utt_len;
-  const int32_t* order;
-  const nnk_chain_t* chains;
-  int n_utt, n_chain, n_groups, max_T, urank0;
-  double* ws;
-  unsigned long long* status;
-  WinTab<NW, L, U> win;
-};
 
 __device__ __forceinline__ double load_go(const void* go, int is_f64, int64_t idx) {
   return is_f64 ? ld_stream(reinterpret_cast<const double*>(go) + idx)
@@ -346,6 +318,13 @@ static int pick_instance(const nnk_windows_t& w, int& inst) {
   return 2 * NNK_MAX_HALF;
 }
 
+// NNK_MLPG_DIRECT=1 selects the register-prefetch kernel for A/B measurements (both are CUDA paths)
+static bool force_direct_loads() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NNK_MLPG_DIRECT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 template <typename Tin, int NW, int L, int U, int MODE>
 static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   constexpr int NT = L + U + 1;
@@ -361,10 +340,18 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   size_t items_cap = per_item ? a.workspace_bytes / per_item : 0;
   int utt_per_launch = (int)(items_cap / (size_t)p.n_groups);
   if (utt_per_launch < 1) { set_error("workspace too small: need >= %zu bytes", per_item * p.n_groups); return NNK_ERR_WORKSPACE; }
+  // forward solves go through the TMA-staged kernel unless the rows are too wide for its ring
+  TmaGeom geom;
+  size_t smem_bytes = 0;
+  const bool staged = (MODE == MODE_FWD) && !force_direct_loads() &&
+                      tma_geometry(a.in_ld, a.var_ld, (int)sizeof(Tin), NT, geom, smem_bytes);
   for (int u0 = 0; u0 < a.n_utt; u0 += utt_per_launch) {
     const int nu = (a.n_utt - u0 < utt_per_launch) ? a.n_utt - u0 : utt_per_launch;
     p.urank0 = u0;
-    mlpg_kernel<Tin, NW, L, U, MODE, PF><<<nu * p.n_groups, 32, 0, st>>>(p);
+    if (staged)
+      mlpg_fwd_tma_kernel<Tin, NW, L, U><<<nu * p.n_groups, 32, smem_bytes, st>>>(p, geom);
+    else
+      mlpg_kernel<Tin, NW, L, U, MODE, PF><<<nu * p.n_groups, 32, 0, st>>>(p);
     count_launch();
     NNK_CUDA_CHECK(cudaGetLastError());
   }

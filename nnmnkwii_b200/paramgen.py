@@ -129,7 +129,7 @@ def _np_dtype_code(dt):
     return None
 
 
-def mlpg_batch(means, variances, windows, lengths=None, offsets=None, layout=None, check=True):
+def mlpg_batch(means, variances, windows, lengths=None, offsets=None, layout=None, check=True, out=None):
     """Batched MLPG over many utterances and streams in one call (additive API).
 
     Args:
@@ -139,6 +139,8 @@ def mlpg_batch(means, variances, windows, lengths=None, offsets=None, layout=Non
         variances: same shape as ``means`` (per-frame) or ``(D,)`` (global).
         windows: list of ``(l, u, coeff)`` triples shared by all smoothed streams.
         layout: :class:`StreamLayout`; default = one stream covering all columns.
+        out: optional preallocated ``(sum_T, D_out)`` NumPy result buffer of the input dtype (flat
+            host form only); pass page-locked memory to keep the device-to-host copy asynchronous.
 
     Returns:
         ``(sum_T, D_out)`` (or ``(B, Tmax, D_out)``) array / tensor of the input dtype.
@@ -179,7 +181,10 @@ def mlpg_batch(means, variances, windows, lengths=None, offsets=None, layout=Non
     n_rows = m.shape[0]
     off = _offsets_from(lengths, offsets, n_rows)
     assert off[0] == 0 and off[-1] == n_rows
-    out = np.zeros((n_rows, layout.D_out), dtype=work_dtype)
+    if out is not None and (out.shape != (n_rows, layout.D_out) or out.dtype != work_dtype or not out.flags.c_contiguous):
+        raise ValueError("out must be a C-contiguous (%d, %d) array of dtype %s" % (n_rows, layout.D_out, work_dtype))
+    if out is None:
+        out = np.empty((n_rows, layout.D_out), dtype=work_dtype)
     st = _lib.NnkStatus()
     chains = np.ascontiguousarray(layout.chains)
     rc = _lib.lib.nnk_mlpg_batch_host(
