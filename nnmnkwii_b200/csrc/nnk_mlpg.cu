@@ -325,6 +325,12 @@ static bool force_direct_loads() {
   return v == 1;
 }
 
+static bool is_std_windows(const nnk_windows_t& w) {
+  if (w.nw != 3 || w.l[0] != 0 || w.u[0] != 0 || w.l[1] != 1 || w.u[1] != 1 || w.l[2] != 1 || w.u[2] != 1) return false;
+  return w.coef[0][0] == 1.0 && w.coef[1][0] == -0.5 && w.coef[1][1] == 0.0 && w.coef[1][2] == 0.5 &&
+         w.coef[2][0] == 1.0 && w.coef[2][1] == -2.0 && w.coef[2][2] == 1.0;
+}
+
 template <typename Tin, int NW, int L, int U, int MODE>
 static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   constexpr int NT = L + U + 1;
@@ -343,13 +349,25 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   // forward solves go through the TMA-staged kernel unless the rows are too wide for its ring
   TmaGeom geom;
   size_t smem_bytes = 0;
-  const bool staged = (MODE == MODE_FWD) && !force_direct_loads() &&
-                      tma_geometry(a.in_ld, a.var_ld, (int)sizeof(Tin), NT, geom, smem_bytes);
+  constexpr int TT = 4, NS = 4, TTB = 4;
+  const bool staged = (MODE == MODE_FWD) && !force_direct_loads() && (a.win.nw == NW) &&
+                      tma_geometry<TT, NS, TTB>(a.in_ld, a.var_ld, (int)sizeof(Tin), NT, geom, smem_bytes);
   for (int u0 = 0; u0 < a.n_utt; u0 += utt_per_launch) {
     const int nu = (a.n_utt - u0 < utt_per_launch) ? a.n_utt - u0 : utt_per_launch;
     p.urank0 = u0;
-    if (staged)
-      mlpg_fwd_tma_kernel<Tin, NW, L, U><<<nu * p.n_groups, 32, smem_bytes, st>>>(p, geom);
+    if (staged) {
+      constexpr bool CAN_STD = (NW == 3 && L == 1 && U == 1);
+      const bool stdw = CAN_STD && is_std_windows(a.win);
+      const bool varg = (a.var_ld == 0);
+      const int grid = nu * p.n_groups;
+#define NNK_LAUNCH_TMA(STDV, VARGV) \
+  mlpg_fwd_tma_kernel<Tin, NW, L, U, STDV, VARGV, TT, NS, TTB><<<grid, 32, smem_bytes, st>>>(p, geom)
+      if (stdw && !varg) NNK_LAUNCH_TMA(CAN_STD, false);
+      else if (stdw && varg) NNK_LAUNCH_TMA(CAN_STD, true);
+      else if (!varg) NNK_LAUNCH_TMA(false, false);
+      else NNK_LAUNCH_TMA(false, true);
+#undef NNK_LAUNCH_TMA
+    }
     else
       mlpg_kernel<Tin, NW, L, U, MODE, PF><<<nu * p.n_groups, 32, 0, st>>>(p);
     count_launch();

@@ -43,6 +43,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // bounded spin: a lost transaction must become an error, never a hung GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (unsigned spin = 0; spin < (1u << 28); ++spin)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
@@ -54,12 +55,51 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 struct TmaGeom {
-  int TT, NS, TTB;       // frames per input tile, ring depth, frames per scratch tile
-  uint32_t sb_in;        // bytes of one input stage (one array)
-  uint32_t sb_ws;        // bytes of one scratch stage
+  uint32_t sb_in;  // bytes of one input stage (one array)
+  uint32_t sb_ws;  // bytes of one scratch stage
 };
 
-template <typename Tin, int NW, int L, int U>
+// reciprocal of a positive, normal double: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps.
+// Not correctly rounded (<= 1 ulp); the pivots it inverts are only used inside the factorisation.
+__device__ __forceinline__ double rcp_pos(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
+// 1 / v in the INPUT dtype like the reference (paramgen/_mlpg.py:188).  float: MUFU.RCP + one
+// Newton step in FMA -- the in-range path of the IEEE-rounded __frcp_rn, without its special-case
+// branch (variances are finite, normal, non-zero numbers); double: IEEE division.
+template <bool B> struct FullTile { static constexpr bool value = B; };
+
+template <typename T> struct recip_fast;
+template <> struct recip_fast<float> {
+  static __device__ __forceinline__ double f(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    const float e = fmaf(-v, r, 1.0f);
+    r = fmaf(r, e, r);
+    return (double)r;
+  }
+};
+template <> struct recip_fast<double> {
+  static __device__ __forceinline__ double f(double v) { return __drcp_rn(v); }
+};
+
+// STD: the window set is exactly static / [-0.5, 0, 0.5] / [1, -2, 1] (HTS, Merlin, the reference's
+// docs and tests): the band rows are assembled from closed-form expressions instead of the generic
+// coefficient tables.  VARG: global (D,) variances (var_ld == 0).  The kernel requires nw == NW.
+//
+// Every lane executes the same instruction stream: idle lanes (chain >= n_chain) and pass-through
+// lanes read clamped in-tile addresses and solve a dummy chain whose results are never stored, so
+// the hot loop has no divergent branches.  Interior tiles (TT real frames, no edge frames, no
+// skipped rows) run the branch-free FULL path; the first / last tiles and the drain run the same
+// code with the per-frame predicates enabled.
+template <typename Tin, int NW, int L, int U, bool STD, bool VARG, int TT, int NS, int TTB>
 __global__ void __launch_bounds__(32) mlpg_fwd_tma_kernel(const __grid_constant__ MlpgParams<Tin, NW, L, U> p,
                                                           const TmaGeom g) {
   constexpr int S = L + U;
@@ -84,16 +124,15 @@ __global__ void __launch_bounds__(32) mlpg_fwd_tma_kernel(const __grid_constant_
   if (active) ch = p.chains[chain];
   const bool copy_lane = active && (ch.flags & 1);
   const bool solve = active && !(ch.flags & 1);
-  const int nw = p.win.nw;
   const int m_edge = p.win.m_edge;
-  const bool var_global = (p.var_ld == 0);
-  const int NS = g.NS, TT = g.TT, TTB = g.TTB;
 
-  // column span of this warp
-  int lo_c = active ? ch.in_col : INT_MAX;
-  int hi_c = active ? ch.in_col + (solve ? (nw - 1) * ch.win_stride : 0) : -1;
+  // column span of this warp; idle lanes are clamped onto it
+  const int lo_c = active ? ch.in_col : INT_MAX;
+  const int hi_c = active ? ch.in_col + (solve ? (NW - 1) * ch.win_stride : 0) : -1;
   const int cmin = __reduce_min_sync(0xffffffffu, lo_c);
   const int cmax = __reduce_max_sync(0xffffffffu, hi_c);
+  const int my_col = active ? ch.in_col : cmin;
+  const int my_stride = solve ? ch.win_stride : 0;
 
   if (lane == 0) {
     for (int s = 0; s < 2 * NS; ++s) mbar_init(bars + s, 1);
@@ -102,44 +141,43 @@ __global__ void __launch_bounds__(32) mlpg_fwd_tma_kernel(const __grid_constant_
   }
   __syncwarp();
 
-  const unsigned char* mbase = reinterpret_cast<const unsigned char*>(p.means);
-  const unsigned char* vbase = reinterpret_cast<const unsigned char*>(p.vars);
   const int ntile = (T + TT - 1) / TT;
+  const int ldb_m = (int)(p.in_ld * ES), ldb_v = (int)(p.var_ld * ES);  // row strides in bytes
+  // global byte address of (frame 0, column cmin) of this utterance
+  const uint64_t g_m = (uint64_t)p.means + (uint64_t)((row0 * p.in_ld + cmin) * ES);
+  const uint64_t g_v = (uint64_t)p.vars + (uint64_t)((VARG ? 0 : row0 * p.var_ld + cmin) * ES);
+  const uint32_t span_b = (uint32_t)(cmax - cmin + 1) * ES;
 
-  // byte range of input tile k in `base` (row stride ld elements), widened to 16-byte alignment
-  auto tile_range = [&](const unsigned char* base, int64_t ld, int k, uint64_t& a0, uint32_t& bytes, uint32_t& mis) {
-    const int t0 = k * TT, t1 = min(T, t0 + TT);
-    const uint64_t A0 = (uint64_t)base + (uint64_t)(((row0 + t0) * ld + cmin) * ES);
-    const uint64_t A1 = (uint64_t)base + (uint64_t)(((row0 + t1 - 1) * ld + cmax + 1) * ES);
-    a0 = A0 & ~(uint64_t)15;
-    bytes = (uint32_t)(((A1 + 15) & ~(uint64_t)15) - a0);
-    mis = (uint32_t)(A0 - a0);
-  };
-  auto issue_in = [&](int k) {  // lane 0 only
-    const int s = k % NS;
-    uint64_t a0, b0 = 0; uint32_t nb, nb2 = 0, mis;
-    tile_range(mbase, p.in_ld, k, a0, nb, mis);
-    if (!var_global) tile_range(vbase, p.var_ld, k, b0, nb2, mis);
+  auto issue_in = [&](int k, int s) {  // lane 0 only: tile k -> stage s
+    const int nfr = min(TT, T - k * TT);
+    const uint64_t A0 = g_m + (uint64_t)((int64_t)k * TT * ldb_m);
+    const uint64_t a0 = A0 & ~(uint64_t)15;
+    const uint32_t nb = (uint32_t)(((A0 + (uint64_t)((nfr - 1) * (int64_t)ldb_m) + span_b + 15) & ~(uint64_t)15) - a0);
+    uint32_t nb2 = 0;
+    uint64_t b0 = 0;
+    if (!VARG) {
+      const uint64_t B0 = g_v + (uint64_t)((int64_t)k * TT * ldb_v);
+      b0 = B0 & ~(uint64_t)15;
+      nb2 = (uint32_t)(((B0 + (uint64_t)((nfr - 1) * (int64_t)ldb_v) + span_b + 15) & ~(uint64_t)15) - b0);
+    }
     mbar_expect_tx(bars + s, nb + nb2);
     bulk_g2s(ring + (size_t)s * 2 * g.sb_in, reinterpret_cast<const void*>(a0), nb, bars + s);
-    if (!var_global) bulk_g2s(ring + (size_t)s * 2 * g.sb_in + g.sb_in, reinterpret_cast<const void*>(b0), nb2, bars + s);
+    if (!VARG) bulk_g2s(ring + (size_t)s * 2 * g.sb_in + g.sb_in, reinterpret_cast<const void*>(b0), nb2, bars + s);
   };
   if (lane == 0)
-    for (int k = 0; k < NS && k < ntile; ++k) issue_in(k);
+    for (int k = 0; k < NS && k < ntile; ++k) issue_in(k, k);
 
-  Tin gv[NW];
+  // global variances: tau is constant over time (up to the edge rule)
+  double gtau[NW];
 #pragma unroll
   for (int w = 0; w < NW; ++w)
-    gv[w] = (solve && var_global && w < nw) ? p.vars[ch.in_col + w * ch.win_stride] : Tin(1);
+    gtau[w] = VARG ? recip_in_dtype<Tin>::f(p.vars[my_col + w * my_stride]) : 0.0;
 
-  double* ws = p.ws + (size_t)item * ((size_t)p.max_T * NT * 32);
+  double* const ws0 = p.ws + (size_t)item * ((size_t)p.max_T * NT * 32);
+  double* wsp = ws0 + lane;
+  Tin* const outp = reinterpret_cast<Tin*>(p.out) + row0 * p.out_ld + ch.out_col;
 
   // ---- forward sweep ---------------------------------------------------------------------------
-  double wt[NT][NW], wm[NT][NW];  // wt[i] = tau of frame (t + L - i)
-#pragma unroll
-  for (int i = 0; i < NT; ++i)
-#pragma unroll
-    for (int w = 0; w < NW; ++w) { wt[i][w] = 0.0; wm[i][w] = 0.0; }
   double vcol[S + 1][S + 1], lcol[S + 1][S + 1], zz[S + 1];
 #pragma unroll
   for (int k = 0; k <= S; ++k) {
@@ -148,26 +186,10 @@ __global__ void __launch_bounds__(32) mlpg_fwd_tma_kernel(const __grid_constant_
     for (int j = 0; j <= S; ++j) { vcol[k][j] = 0.0; lcol[k][j] = 0.0; }
   }
   double iv1 = 0.0;
-  bool reported = false;
-  Tin* outp = reinterpret_cast<Tin*>(p.out) + row0 * p.out_ld + ch.out_col;
+  int bad = 0;  // 1-based frame of the first non-positive pivot of this chain
 
-  // one elimination step for row t, with the window already holding frames t-U .. t+L
-  auto step = [&](int t) {
-    double acc[S + 1];
-#pragma unroll
-    for (int m = 0; m <= S; ++m) {
-      double a = 0.0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w)
-#pragma unroll
-        for (int i = 0; i + m < NT; ++i) a = fma(p.win.q[w][m][i], wt[i][w], a);
-      acc[m] = a;
-    }
-    double bb = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w)
-#pragma unroll
-      for (int i = 0; i < NT; ++i) bb = fma(p.win.c[w][i], wm[i][w], bb);
+  // eliminate row t given its assembled band row acc[m] = P[t][t+m] and right-hand side bb
+  auto eliminate = [&](int t, double(&acc)[S + 1], double bb) {
 #pragma unroll
     for (int k = 2; k <= S; ++k) {
 #pragma unroll
@@ -180,18 +202,14 @@ __global__ void __launch_bounds__(32) mlpg_fwd_tma_kernel(const __grid_constant_
       bb = fma(-(vcol[1][1] * zz[1]), iv1, bb);
     }
     const double d = acc[0];
-    if (!(d > 0.0) && solve && !reported) {  // linalg.pyx:79-82
-      reported = true;
-      report_not_pd(p.status, utt, chain, t + 1);
-    }
-    const double ivd = __drcp_rn(d);
-    double* wsp = ws + (size_t)t * (NT * 32) + lane;
+    bad = (bad == 0 && !(d > 0.0)) ? t + 1 : bad;  // linalg.pyx:79-82, reported after the sweep
+    const double ivd = rcp_pos(d);
     wsp[0] = bb * ivd;
 #pragma unroll
-    for (int k = S; k >= 2; --k) {
+    for (int k = S; k >= 2; --k) {  // only the entries later rows still need are carried
       zz[k] = zz[k - 1];
 #pragma unroll
-      for (int j = 0; j <= S; ++j) { vcol[k][j] = vcol[k - 1][j]; lcol[k][j] = lcol[k - 1][j]; }
+      for (int j = k; j <= S; ++j) { vcol[k][j] = vcol[k - 1][j]; lcol[k][j] = lcol[k - 1][j]; }
     }
     if (S >= 1) {
       zz[1] = bb;
@@ -204,63 +222,122 @@ __global__ void __launch_bounds__(32) mlpg_fwd_tma_kernel(const __grid_constant_
       }
       iv1 = ivd;
     }
-  };
-  auto push_frame = [&](int f, const Tin(&m)[NW], const Tin(&v)[NW]) {
-#pragma unroll
-    for (int i = NT - 1; i > 0; --i)
-#pragma unroll
-      for (int w = 0; w < NW; ++w) { wt[i][w] = wt[i - 1][w]; wm[i][w] = wm[i - 1][w]; }
-    const bool in = (f < T);
-    const bool edge = (m_edge == 0) || (f < m_edge) || (f >= T - m_edge);
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const bool on = in && solve && (w < nw) && !(w > 0 && edge);
-      const double tw = on ? recip_in_dtype<Tin>::f(v[w]) : 0.0;
-      wt[0][w] = tw;
-      wm[0][w] = tw * (double)m[w];
-    }
+    wsp += NT * 32;
   };
 
-  for (int k = 0; k < ntile; ++k) {
-    const int s = k % NS;
-    mbar_wait(bars + s, (uint32_t)((k / NS) & 1));
-    const int t0 = k * TT, t1 = min(T, t0 + TT);
-    const unsigned char* sm_m = ring + (size_t)s * 2 * g.sb_in;
-    const unsigned char* sm_v = sm_m + g.sb_in;
-    const uint32_t mis_m = (uint32_t)(((uint64_t)mbase + (uint64_t)(((row0 + t0) * p.in_ld + cmin) * ES)) & 15);
-    const uint32_t mis_v = var_global ? 0u : (uint32_t)(((uint64_t)vbase + (uint64_t)(((row0 + t0) * p.var_ld + cmin) * ES)) & 15);
-    for (int f = t0; f < t1; ++f) {
-      Tin m[NW], v[NW];
+  // carry[i] = frame (t0 - (NT-1) + i) of the previous tile (oldest first)
+  constexpr int NC = NT - 1 > 0 ? NT - 1 : 1;
+  double cft[NC][NW], cfm[NC][NW];
 #pragma unroll
-      for (int w = 0; w < NW; ++w) { m[w] = Tin(0); v[w] = Tin(1); }
-      if (active) {
-        const int64_t rm = (int64_t)(f - t0) * p.in_ld - cmin + ch.in_col;
-        const int64_t rv = (int64_t)(f - t0) * p.var_ld - cmin + ch.in_col;
+  for (int i = 0; i < NC; ++i)
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          if (w < nw && (solve || w == 0)) {
-            m[w] = *reinterpret_cast<const Tin*>(sm_m + mis_m + (rm + w * ch.win_stride) * ES);
-            if (solve) v[w] = var_global ? gv[w] : *reinterpret_cast<const Tin*>(sm_v + mis_v + (rv + w * ch.win_stride) * ES);
-          }
-        }
+    for (int w = 0; w < NW; ++w) { cft[i][w] = 0.0; cfm[i][w] = 0.0; }
+
+  // byte offsets of this lane's NW columns inside a staged row
+  int colb[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) colb[w] = (my_col - cmin + w * my_stride) * ES;
+
+  // A tile is processed in three phases so that the independent work of TT frames (loads,
+  // reciprocals, assembly of the band rows) is issued back to back and only the short elimination
+  // recurrence is serial: (1) frames -> (tau, tau*mu); (2) band rows of P and b; (3) eliminate.
+  // FULL: TT real interior frames (no edge rule, no skipped rows); otherwise nfr real frames are
+  // staged and nproc frames are consumed (zeros past the end).
+  auto do_tile = [&](auto full_tag, int t0, int nfr, int nproc, const unsigned char* sm_m, const unsigned char* sm_v) {
+    constexpr bool FULL = decltype(full_tag)::value;
+    double ft[TT + NT - 1][NW], fm[TT + NT - 1][NW];
+#pragma unroll
+    for (int i = 0; i < NT - 1; ++i)
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { ft[i][w] = cft[i][w]; fm[i][w] = cfm[i][w]; }
+    // phase 1
+#pragma unroll
+    for (int j = 0; j < TT; ++j) {
+      const int f = t0 + j;
+      const bool real = FULL || (j < nfr);
+      const bool edge = !FULL && ((m_edge == 0) || (f < m_edge) || (f >= T - m_edge));
+      const int jj = real ? j : 0;  // keep the address inside the stage for frames past the end
+      Tin mraw[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) mraw[w] = *reinterpret_cast<const Tin*>(sm_m + jj * ldb_m + colb[w]);
+      if (copy_lane && real) st_stream(outp + (int64_t)f * p.out_ld, mraw[0]);  // pass-through column
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        double tw;
+        if (VARG) tw = gtau[w];
+        else tw = recip_fast<Tin>::f(*reinterpret_cast<const Tin*>(sm_v + jj * ldb_v + colb[w]));
+        if (!FULL) tw = (!real || (w > 0 && edge)) ? 0.0 : tw;
+        ft[NT - 1 + j][w] = tw;
+        fm[NT - 1 + j][w] = tw * (double)mraw[w];
       }
-      if (copy_lane) st_stream(outp + (int64_t)f * p.out_ld, m[0]);  // pass-through column
-      push_frame(f, m, v);
-      if (f >= L) step(f - L);
     }
-    __syncwarp();
-    if (lane == 0 && k + NS < ntile) issue_in(k + NS);
-  }
-  {  // drain: the last L rows see zero frames beyond the end
-    Tin m[NW], v[NW];
+    // phase 2: row (t0 + j - L) sees frame (t0 + j - i) in window slot i  ->  ft[NT-1 + j - i]
+    double acc[TT][S + 1], bb[TT];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) { m[w] = Tin(0); v[w] = Tin(1); }
+    for (int j = 0; j < TT; ++j) {
+      if (STD) {
+        // static / delta [-0.5, 0, 0.5] / delta-delta [1, -2, 1]: the band row in closed form
+        const double* a = ft[j];      // frame t-1
+        const double* b = ft[j + 1];  // frame t
+        const double* c = ft[j + 2];  // frame t+1
+        acc[j][0] = b[0] + fma(0.25, a[1] + c[1], fma(4.0, b[2], a[2] + c[2]));
+        acc[j][1] = -2.0 * (b[2] + c[2]);
+        acc[j][2] = fma(-0.25, c[1], c[2]);
+        bb[j] = fm[j + 1][0] + fma(0.5, fm[j][1] - fm[j + 2][1], fma(-2.0, fm[j + 1][2], fm[j][2] + fm[j + 2][2]));
+      } else {
 #pragma unroll
-    for (int e = 0; e < L; ++e) {
-      push_frame(T + e, m, v);
-      if (T + e >= L) step(T + e - L);
+        for (int m = 0; m <= S; ++m) {
+          double a = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int i = 0; i + m < NT; ++i) a = fma(p.win.q[w][m][i], ft[NT - 1 + j - i][w], a);
+          acc[j][m] = a;
+        }
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+          for (int i = 0; i < NT; ++i) r = fma(p.win.c[w][i], fm[NT - 1 + j - i][w], r);
+        bb[j] = r;
+      }
     }
+    // phase 3
+#pragma unroll
+    for (int j = 0; j < TT; ++j)
+      if (FULL || (j < nproc && t0 + j >= L)) eliminate(t0 + j - L, acc[j], bb[j]);
+    // carry the last NT-1 frames
+#pragma unroll
+    for (int i = 0; i < NT - 1; ++i)
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { cft[i][w] = ft[TT + i][w]; cfm[i][w] = fm[TT + i][w]; }
+  };
+
+  {
+    int s = 0;
+    uint32_t par = 0;
+    uint32_t mis_m = (uint32_t)(g_m & 15), mis_v = (uint32_t)(g_v & 15);  // misalignment of the current tile
+    const uint32_t dmis_m = (uint32_t)(TT * ldb_m) & 15, dmis_v = (uint32_t)(TT * ldb_v) & 15;
+    const int full_lo = max(L, m_edge), full_hi = (m_edge > 0) ? T - m_edge : -1;
+    for (int k = 0; k < ntile; ++k) {
+      mbar_wait(bars + s, par);
+      const int t0 = k * TT;
+      const unsigned char* sm_m = ring + (size_t)s * 2 * g.sb_in + mis_m;
+      const unsigned char* sm_v = ring + (size_t)s * 2 * g.sb_in + g.sb_in + mis_v;
+      if (t0 >= full_lo && t0 + TT <= full_hi)
+        do_tile(FullTile<true>{}, t0, TT, TT, sm_m, sm_v);
+      else
+        do_tile(FullTile<false>{}, t0, min(TT, T - t0), min(TT, T + L - t0), sm_m, sm_v);
+      __syncwarp();
+      if (lane == 0 && k + NS < ntile) issue_in(k + NS, s);
+      mis_m = (mis_m + dmis_m) & 15;
+      mis_v = (mis_v + dmis_v) & 15;
+      if (++s == NS) { s = 0; par ^= 1; }
+    }
+    // drain: the last L rows see only zero frames beyond the end
+    if (ntile * TT < T + L) do_tile(FullTile<false>{}, ntile * TT, 0, T + L - ntile * TT, ring, ring);
   }
+  if (bad && solve) report_not_pd(p.status, utt, chain, bad);
 
   // ---- backward sweep: y[t] = zs[t] - sum_j l_j[t] y[t+j] -----------------------------------------
   // the factor scratch was written with ordinary stores; order them before the async-proxy reads
@@ -269,59 +346,59 @@ __global__ void __launch_bounds__(32) mlpg_fwd_tma_kernel(const __grid_constant_
   __syncwarp();
   uint64_t* bbar = bars + NS;
   const int nbt = (T + TTB - 1) / TTB;
-  auto issue_ws = [&](int kb) {  // lane 0 only; tiles are consumed from the last to the first
-    const int idx = nbt - 1 - kb;
-    const int s = kb % NS;
-    const int t0 = idx * TTB, t1 = min(T, t0 + TTB);
-    const uint32_t nb = (uint32_t)(t1 - t0) * NT * 32 * 8;
+  auto issue_ws = [&](int kb, int s) {  // lane 0 only; tiles are consumed from the last to the first
+    const int t0 = (nbt - 1 - kb) * TTB;
+    const uint32_t nb = (uint32_t)(min(T, t0 + TTB) - t0) * NT * 32 * 8;
     mbar_expect_tx(bbar + s, nb);
-    bulk_g2s(ring + (size_t)s * g.sb_ws, ws + (size_t)t0 * (NT * 32), nb, bbar + s);
+    bulk_g2s(ring + (size_t)s * g.sb_ws, ws0 + (size_t)t0 * (NT * 32), nb, bbar + s);
   };
   if (lane == 0)
-    for (int kb = 0; kb < NS && kb < nbt; ++kb) issue_ws(kb);
+    for (int kb = 0; kb < NS && kb < nbt; ++kb) issue_ws(kb, kb);
   double yw[S + 1];
 #pragma unroll
   for (int j = 0; j <= S; ++j) yw[j] = 0.0;
-  for (int kb = 0; kb < nbt; ++kb) {
-    const int s = kb % NS;
-    mbar_wait(bbar + s, (uint32_t)((kb / NS) & 1));
-    const int idx = nbt - 1 - kb;
-    const int t0 = idx * TTB, t1 = min(T, t0 + TTB);
-    const double* smw = reinterpret_cast<const double*>(ring + (size_t)s * g.sb_ws) + lane;
-    for (int t = t1 - 1; t >= t0; --t) {
-      const double* fr = smw + (size_t)(t - t0) * (NT * 32);
+  auto back = [&](int t, const double* fr) {
 #pragma unroll
-      for (int j = S; j > 0; --j) yw[j] = yw[j - 1];
-      double y = fr[0];
+    for (int j = S; j > 0; --j) yw[j] = yw[j - 1];
+    double y = fr[0];
 #pragma unroll
-      for (int j = 1; j <= S; ++j) y = fma(-fr[j * 32], yw[j], y);
-      yw[0] = y;
-      if (solve) st_stream(outp + (int64_t)t * p.out_ld, (Tin)y);
+    for (int j = 1; j <= S; ++j) y = fma(-fr[j * 32], yw[j], y);
+    yw[0] = y;
+    if (solve) st_stream(outp + (int64_t)t * p.out_ld, (Tin)y);
+  };
+  {
+    int s = 0;
+    uint32_t par = 0;
+    for (int kb = 0; kb < nbt; ++kb) {
+      mbar_wait(bbar + s, par);
+      const int t0 = (nbt - 1 - kb) * TTB;
+      const double* smw = reinterpret_cast<const double*>(ring + (size_t)s * g.sb_ws) + lane;
+      if (t0 + TTB <= T) {
+#pragma unroll
+        for (int j = TTB - 1; j >= 0; --j) back(t0 + j, smw + j * (NT * 32));
+      } else {
+        for (int t = T - 1; t >= t0; --t) back(t, smw + (t - t0) * (NT * 32));
+      }
+      __syncwarp();
+      if (lane == 0 && kb + NS < nbt) issue_ws(kb + NS, s);
+      if (++s == NS) { s = 0; par ^= 1; }
     }
-    __syncwarp();
-    if (lane == 0 && kb + NS < nbt) issue_ws(kb + NS);
   }
 }
 
 // ring geometry for a given row stride; returns false if the rows are too wide for the staged kernel
+template <int TT, int NS, int TTB>
 static inline bool tma_geometry(int64_t in_ld, int64_t var_ld, int es, int nt, TmaGeom& g, size_t& smem_bytes) {
   const int64_t ld = in_ld > var_ld ? in_ld : var_ld;
-  g.NS = 4;
-  g.TTB = 4;
-  for (int TT = 8; TT >= 2; TT /= 2) {
-    g.TT = TT;
-    const size_t sb_in = ((size_t)TT * (size_t)ld * es + 32 + 15) / 16 * 16;
-    const size_t sb_ws = (size_t)g.TTB * nt * 32 * 8;
-    const size_t fwd = (size_t)g.NS * 2 * sb_in, bwd = (size_t)g.NS * sb_ws;
-    const size_t tot = 128 + (fwd > bwd ? fwd : bwd);
-    if (tot <= (size_t)40 * 1024) {
-      g.sb_in = (uint32_t)sb_in;
-      g.sb_ws = (uint32_t)sb_ws;
-      smem_bytes = tot;
-      return true;
-    }
-  }
-  return false;
+  const size_t sb_in = ((size_t)TT * (size_t)ld * es + 32 + 15) / 16 * 16;
+  const size_t sb_ws = (size_t)TTB * nt * 32 * 8;
+  const size_t fwd = (size_t)NS * 2 * sb_in, bwd = (size_t)NS * sb_ws;
+  const size_t tot = 128 + (fwd > bwd ? fwd : bwd);
+  if (tot > (size_t)40 * 1024) return false;
+  g.sb_in = (uint32_t)sb_in;
+  g.sb_ws = (uint32_t)sb_ws;
+  smem_bytes = tot;
+  return true;
 }
 
 }  // namespace nnk
