@@ -330,6 +330,12 @@ def run_ours(args):
     if rank == 0:
         assert np.array_equal(y[: int(off_np[1])], d_out[: int(off_np[1])].cpu().numpy()), "e2e and device paths disagree"
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            extras = bench_extras(device)
+        except Exception as e:  # the headline line must survive a failure of the side measurements
+            extras = {"error": repr(e)}
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         dist.barrier()
@@ -356,8 +362,72 @@ def run_ours(args):
         "allgather_ms": ag_ms,
         "parity_max_rel_err_vs_oracle": parity,
         "frames_per_step_per_gpu": n_rows,
+        "other_kernels": extras,
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# the other kernels of the path (reported as extra keys next to the headline metric)
+# ---------------------------------------------------------------------------------------------------
+def make_dtw_pairs(n_pairs, seed=4321):
+    """configs[3]: random MFCC-like 25-dim pairs, T~U{700..900}; Y = monotone time-warp of X + noise."""
+    rng = np.random.default_rng(seed)
+    D, Tmax = 25, 900
+    X = np.zeros((n_pairs, Tmax, D), np.float32)
+    Y = np.zeros((n_pairs, Tmax, D), np.float32)
+    for n in range(n_pairs):
+        Tx, Ty = int(rng.integers(700, 901)), int(rng.integers(700, 901))
+        x = (np.cumsum(rng.standard_normal((Tx, D)), 0) * 0.1).astype(np.float32)
+        src = np.sort(rng.random(Ty)) * (Tx - 1)
+        y = x[np.round(src).astype(int)] + 0.05 * rng.standard_normal((Ty, D)).astype(np.float32)
+        X[n, :Tx], Y[n, :Ty] = x, y
+    return X, Y
+
+
+def bench_extras(device, reps=5):
+    import torch
+    from nnmnkwii_b200 import autograd as AF
+    from nnmnkwii_b200 import paramgen as G
+    from nnmnkwii_b200.preprocessing import alignment as A
+    out = {}
+    # --- DTW, configs[3]: 512 pairs, melcd cost ------------------------------------------------------
+    X, Y = make_dtw_pairs(512)
+    Xd, Yd = torch.from_numpy(X).to(device), torch.from_numpy(Y).to(device)
+    for name, radius in (("fastdtw_radius1", 1), ("exact", -1)):
+        res = A._align_batch(Xd, Yd, 1, radius)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            res = A._align_batch(Xd, Yd, 1, radius)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        cells = int(res.cells.sum().item())
+        out["dtw_" + name] = {"cell_updates_per_sec": cells / (ms * 1e-3), "cells_per_batch": cells, "pairs": 512,
+                              "ms_per_batch": ms, "cost": "melcd", "includes": "trim + DTW (no gather)"}
+    # --- UnitVarianceMLPG fwd + loss.backward(), configs[2] ---------------------------------------------
+    T, sd, B = 1000, 60, 64
+    R = torch.from_numpy(G.unit_variance_mlpg_matrix(WINDOWS, T)).to(device)
+    g = torch.Generator(device=device).manual_seed(0)
+    mu = torch.randn(B, T, 3 * sd, device=device, generator=g).requires_grad_(True)
+    for _ in range(2):
+        AF.unit_variance_mlpg(R, mu).pow(2).mean().backward()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        mu.grad = None
+        AF.unit_variance_mlpg(R, mu).pow(2).mean().backward()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out["unit_variance_mlpg_fwd_bwd"] = {"frames_per_sec": B * T / (ms * 1e-3), "ms_per_iter": ms, "batch": B, "T": T,
+                                         "static_dim": sd, "algorithmic_bytes": 122.9e6,
+                                         "hbm_gbs_algorithmic": 122.9e6 / (ms * 1e-3) / 1e9,
+                                         "includes": "stencil fwd + loss (torch) + stencil bwd"}
+    return out
 
 
 def main():
@@ -368,6 +438,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
