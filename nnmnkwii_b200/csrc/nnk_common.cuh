@@ -64,4 +64,12 @@ template <> struct recip_in_dtype<double> {
 template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 template <typename T> __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
 
+// predicated streaming store (no branch: idle lanes simply do not store)
+__device__ __forceinline__ void st_stream_if(float* p, float v, bool pred) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q st.global.cs.f32 [%0], %1;\n}" ::"l"(p), "f"(v), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void st_stream_if(double* p, double v, bool pred) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q st.global.cs.f64 [%0], %1;\n}" ::"l"(p), "d"(v), "r"((int)pred) : "memory");
+}
+
 }  // namespace nnk

@@ -22,6 +22,7 @@
 
 #include "nnk_mlpg.cuh"
 #include "nnk_mlpg_tma.cuh"
+#include "nnk_mlpg_as.cuh"
 
 namespace nnk {
 
@@ -325,6 +326,13 @@ static bool force_direct_loads() {
   return v == 1;
 }
 
+// NNK_MLPG_SINGLE=1 selects the single-warp TMA kernel instead of the assembler/solver pair
+static bool force_single_warp() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NNK_MLPG_SINGLE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 static bool is_std_windows(const nnk_windows_t& w) {
   if (w.nw != 3 || w.l[0] != 0 || w.u[0] != 0 || w.l[1] != 1 || w.u[1] != 1 || w.l[2] != 1 || w.u[2] != 1) return false;
   return w.coef[0][0] == 1.0 && w.coef[1][0] == -0.5 && w.coef[1][1] == 0.0 && w.coef[1][2] == 0.5 &&
@@ -349,7 +357,12 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   // forward solves go through the TMA-staged kernel unless the rows are too wide for its ring
   TmaGeom geom;
   size_t smem_bytes = 0;
-  constexpr int TT = 4, NS = 4, TTB = 4;
+  constexpr int TT = 4, NS = 4, TTB = 4, NA = 2, NSA = 2, ND = 4;
+  constexpr int TTB_AS = 8, NSB_AS = 4;  // backward-sweep scratch ring of the paired kernel: 32 frames in flight
+  AsGeom as_geom;
+  size_t as_smem = 0;
+  const bool paired = (MODE == MODE_FWD) && !force_single_warp() && (NT <= 5) &&
+                      as_geometry<TT, NA, NSA, ND, TTB_AS, NSB_AS>(a.in_ld, a.var_ld, (int)sizeof(Tin), NT, as_geom, as_smem);
   const bool staged = (MODE == MODE_FWD) && !force_direct_loads() && (a.win.nw == NW) &&
                       tma_geometry<TT, NS, TTB>(a.in_ld, a.var_ld, (int)sizeof(Tin), NT, geom, smem_bytes);
   for (int u0 = 0; u0 < a.n_utt; u0 += utt_per_launch) {
@@ -360,13 +373,27 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
       const bool stdw = CAN_STD && is_std_windows(a.win);
       const bool varg = (a.var_ld == 0);
       const int grid = nu * p.n_groups;
+      if (paired) {
+#define NNK_LAUNCH_AS(STDV, VARGV)                                                                                   \
+  do {                                                                                                              \
+    auto kern = mlpg_fwd_as_kernel<Tin, NW, L, U, STDV, VARGV, TT, NA, NSA, ND, TTB_AS, NSB_AS>;                           \
+    NNK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)as_smem));         \
+    kern<<<grid, 32 * (NA + 1), as_smem, st>>>(p, as_geom);                                                         \
+  } while (0)
+        if (stdw && !varg) NNK_LAUNCH_AS(CAN_STD, false);
+        else if (stdw && varg) NNK_LAUNCH_AS(CAN_STD, true);
+        else if (!varg) NNK_LAUNCH_AS(false, false);
+        else NNK_LAUNCH_AS(false, true);
+#undef NNK_LAUNCH_AS
+      } else {
 #define NNK_LAUNCH_TMA(STDV, VARGV) \
   mlpg_fwd_tma_kernel<Tin, NW, L, U, STDV, VARGV, TT, NS, TTB><<<grid, 32, smem_bytes, st>>>(p, geom)
-      if (stdw && !varg) NNK_LAUNCH_TMA(CAN_STD, false);
-      else if (stdw && varg) NNK_LAUNCH_TMA(CAN_STD, true);
-      else if (!varg) NNK_LAUNCH_TMA(false, false);
-      else NNK_LAUNCH_TMA(false, true);
+        if (stdw && !varg) NNK_LAUNCH_TMA(CAN_STD, false);
+        else if (stdw && varg) NNK_LAUNCH_TMA(CAN_STD, true);
+        else if (!varg) NNK_LAUNCH_TMA(false, false);
+        else NNK_LAUNCH_TMA(false, true);
 #undef NNK_LAUNCH_TMA
+      }
     }
     else
       mlpg_kernel<Tin, NW, L, U, MODE, PF><<<nu * p.n_groups, 32, 0, st>>>(p);

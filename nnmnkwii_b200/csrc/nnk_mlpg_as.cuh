@@ -1,0 +1,356 @@
+// nnk_mlpg_as.cuh -- warp-specialised MLPG forward kernel: NA ASSEMBLER warps and one SOLVER warp
+// per (utterance, 32-chain group).
+//
+// ncu on the single-warp TMA kernel (profiles/r01_mlpg_v5_*): 141 instructions per frame issued by
+// ONE warp at 3.6 cycles per instruction -- the batch has fewer warps (512) than the chip has warp
+// schedulers (592), so nothing hides the fixed-latency dependencies.  Only ~35 of those
+// instructions (the L D L^T elimination and the substitutions) are inherently serial in time; the
+// rest (shared-memory loads, f32 reciprocals, widening, assembling the band row of P and b) is
+// independent per frame.  This kernel splits the two:
+//
+//   warps A_0..A_{NA-1} (assemblers): tile k (TT frames) belongs to warp k mod NA.  Each warp stages
+//                       its own tiles by TMA (rows k*TT-(NT-1) .. k*TT+TT-1, i.e. including the
+//                       window halo, so tiles are self-contained), converts them to (tau, tau*mu),
+//                       assembles the band rows acc[0..S] = P[t][t..t+S] and b[t] and publishes them as
+//                       float64 through a shared-memory ring (PB ring, ND tiles, full/empty mbarriers);
+//   warp S (solver):    consumes band rows in order, eliminates (L D L^T), forward-substitutes,
+//                       writes the factor scratch, then runs the backward sweep (scratch staged by TMA).
+// A first version with a single assembler was assembler-bound (the solver spun on the PB barrier,
+// profiles/r01_mlpg_v6_*); assembly is parallel in time, so it gets NA warps.
+#pragma once
+#include "nnk_mlpg_tma.cuh"
+
+namespace nnk {
+
+struct AsGeom {
+  uint32_t sb_in;     // bytes of one input stage (one array)
+  uint32_t sb_ws;     // bytes of one scratch stage (backward sweep)
+  uint32_t ring_a;    // bytes of one assembler's input ring
+  uint32_t off_pb;    // byte offset of the PB ring inside dynamic shared memory
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename Tin, int NW, int L, int U, bool STD, bool VARG, int TT, int NA, int NSA, int ND, int TTB, int NSB>
+__global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid_constant__ MlpgParams<Tin, NW, L, U> p,
+                                                                    const AsGeom g) {
+  constexpr int S = L + U;
+  constexpr int NT = S + 1;
+  constexpr int NR = S + 2;        // doubles per published band row: acc[0..S], b
+  constexpr int NF = TT + NT - 1;  // frames an assembler converts per tile (TT + halo)
+  constexpr int ES = (int)sizeof(Tin);
+  extern __shared__ __align__(128) unsigned char smem[];
+  // barriers: input full [NA][NSA] | PB full [ND] | PB empty [ND] | scratch full [NSB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* in_full = bars;
+  uint64_t* pb_full = bars + NA * NSA;
+  uint64_t* pb_empty = pb_full + ND;
+  uint64_t* ws_full = pb_empty + ND;
+  static_assert((NA * NSA + 2 * ND + NSB) * 8 <= 512, "barrier block");
+  unsigned char* rings = smem + 512;                                // NA input rings; ring 0 doubles as the scratch ring
+  double* pb = reinterpret_cast<double*>(smem + g.off_pb);          // [ND][TT][NR][32]
+
+  const int lane = threadIdx.x & 31;
+  const int role = threadIdx.x >> 5;  // 0..NA-1 = assemblers, NA = solver
+  const int item = blockIdx.x;
+  const int urank = p.urank0 + item / p.n_groups;
+  const int grp = item % p.n_groups;
+  const int utt = p.order ? p.order[urank] : urank;
+  const int64_t row0 = p.utt_off[utt];
+  const int T = p.utt_len ? p.utt_len[utt] : (int)(p.utt_off[utt + 1] - row0);
+  if (T <= 0) return;
+  const int chain = grp * 32 + lane;
+  const bool active = chain < p.n_chain;
+  nnk_chain_t ch;
+  ch.in_col = 0; ch.win_stride = 0; ch.out_col = 0; ch.flags = 1;
+  if (active) ch = p.chains[chain];
+  const bool copy_lane = active && (ch.flags & 1);
+  const bool solve = active && !(ch.flags & 1);
+  const int m_edge = p.win.m_edge;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NA * NSA; ++s) mbar_init(in_full + s, 1);
+    for (int s = 0; s < NSB; ++s) mbar_init(ws_full + s, 1);
+    for (int s = 0; s < ND; ++s) { mbar_init(pb_full + s, 32); mbar_init(pb_empty + s, 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int npb = (T + L + TT - 1) / TT;  // band-row tiles: tile k holds rows r = k*TT - L + j, j < TT
+  Tin* const outp = reinterpret_cast<Tin*>(p.out) + row0 * p.out_ld + ch.out_col;
+
+  if (role < NA) {
+    // =============================== assembler warp `role` ===========================================
+    const int lo_c = active ? ch.in_col : INT_MAX;
+    const int hi_c = active ? ch.in_col + (solve ? (NW - 1) * ch.win_stride : 0) : -1;
+    const int cmin = __reduce_min_sync(0xffffffffu, lo_c);
+    const int cmax = __reduce_max_sync(0xffffffffu, hi_c);
+    const int my_col = active ? ch.in_col : cmin;
+    const int my_stride = solve ? ch.win_stride : 0;
+    const int ldb_m = (int)(p.in_ld * ES), ldb_v = (int)(p.var_ld * ES);
+    const uint64_t g_m = (uint64_t)p.means + (uint64_t)((row0 * p.in_ld + cmin) * ES);
+    const uint64_t g_v = (uint64_t)p.vars + (uint64_t)((VARG ? 0 : row0 * p.var_ld + cmin) * ES);
+    const uint32_t span_b = (uint32_t)(cmax - cmin + 1) * ES;
+    unsigned char* ring = rings + (size_t)role * g.ring_a;
+    uint64_t* my_full = in_full + role * NSA;
+
+    // tile k stages frames [f_lo, f_hi) = [max(0, k*TT - (NT-1)), min(T, k*TT + TT))  (never empty)
+    auto issue_in = [&](int k, int s) {  // lane 0 only
+      const int f_lo = max(0, k * TT - (NT - 1)), f_hi = min(T, k * TT + TT);
+      const uint64_t A0 = g_m + (uint64_t)((int64_t)f_lo * ldb_m);
+      const uint64_t a0 = A0 & ~(uint64_t)15;
+      const uint32_t nb = (uint32_t)(((A0 + (uint64_t)((f_hi - f_lo - 1) * (int64_t)ldb_m) + span_b + 15) & ~(uint64_t)15) - a0);
+      uint32_t nb2 = 0;
+      uint64_t b0 = 0;
+      if (!VARG) {
+        const uint64_t B0 = g_v + (uint64_t)((int64_t)f_lo * ldb_v);
+        b0 = B0 & ~(uint64_t)15;
+        nb2 = (uint32_t)(((B0 + (uint64_t)((f_hi - f_lo - 1) * (int64_t)ldb_v) + span_b + 15) & ~(uint64_t)15) - b0);
+      }
+      mbar_expect_tx(my_full + s, nb + nb2);
+      bulk_g2s(ring + (size_t)s * 2 * g.sb_in, reinterpret_cast<const void*>(a0), nb, my_full + s);
+      if (!VARG) bulk_g2s(ring + (size_t)s * 2 * g.sb_in + g.sb_in, reinterpret_cast<const void*>(b0), nb2, my_full + s);
+    };
+    if (lane == 0)
+      for (int i = 0; i < NSA; ++i)
+        if (role + i * NA < npb) issue_in(role + i * NA, i);
+
+    double gtau[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+      gtau[w] = VARG ? recip_in_dtype<Tin>::f(p.vars[my_col + w * my_stride]) : 0.0;
+    int colb[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) colb[w] = (my_col - cmin + w * my_stride) * ES;
+
+    // convert the NF frames of tile k (slot j <-> frame k*TT - (NT-1) + j; staged row = frame - f_lo),
+    // assemble its TT band rows and publish them to PB slot `dst`
+    auto do_tile = [&](auto full_tag, int k, const unsigned char* sm_m, const unsigned char* sm_v, double* dst) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const int fbase = k * TT - (NT - 1);
+      const int f_lo = max(0, fbase);
+      double ft[NF][NW], fm[NF][NW];
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int f = fbase + j;
+        const bool real = FULL || (f >= 0 && f < T);
+        const bool edge = !FULL && ((m_edge == 0) || (f < m_edge) || (f >= T - m_edge));
+        const int row = real ? (FULL ? j : f - f_lo) : 0;
+        Tin mraw[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) mraw[w] = *reinterpret_cast<const Tin*>(sm_m + row * ldb_m + colb[w]);
+        if (j >= NT - 1 && copy_lane && real) st_stream(outp + (int64_t)f * p.out_ld, mraw[0]);  // pass-through column
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          double tw;
+          if (VARG) tw = gtau[w];
+          else tw = recip_fast<Tin>::f(*reinterpret_cast<const Tin*>(sm_v + row * ldb_v + colb[w]));
+          if (!FULL) tw = (!real || (w > 0 && edge)) ? 0.0 : tw;
+          ft[j][w] = tw;
+          fm[j][w] = tw * (double)mraw[w];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < TT; ++j) {
+        double acc[S + 1], bb;
+        if (STD) {
+          const double* a = ft[j];      // frame t-1
+          const double* b = ft[j + 1];  // frame t
+          const double* c = ft[j + 2];  // frame t+1
+          acc[0] = b[0] + fma(0.25, a[1] + c[1], fma(4.0, b[2], a[2] + c[2]));
+          acc[1] = -2.0 * (b[2] + c[2]);
+          acc[2] = fma(-0.25, c[1], c[2]);
+          bb = fm[j + 1][0] + fma(0.5, fm[j][1] - fm[j + 2][1], fma(-2.0, fm[j + 1][2], fm[j][2] + fm[j + 2][2]));
+        } else {
+#pragma unroll
+          for (int m = 0; m <= S; ++m) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+#pragma unroll
+              for (int i = 0; i + m < NT; ++i) a = fma(p.win.q[w][m][i], ft[NT - 1 + j - i][w], a);
+            acc[m] = a;
+          }
+          bb = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int i = 0; i < NT; ++i) bb = fma(p.win.c[w][i], fm[NT - 1 + j - i][w], bb);
+        }
+        double* row = dst + (size_t)j * (NR * 32) + lane;
+#pragma unroll
+        for (int m = 0; m <= S; ++m) row[m * 32] = acc[m];
+        row[(S + 1) * 32] = bb;
+      }
+    };
+
+    int s = 0;
+    uint32_t par = 0;
+    for (int k = role; k < npb; k += NA) {
+      const int ps = k % ND;
+      mbar_wait_parked(pb_empty + ps, (uint32_t)(((k / ND) & 1) ^ 1));  // the solver has drained this PB slot
+      mbar_wait(my_full + s, par);
+      double* dst = pb + (size_t)ps * (TT * NR * 32);
+      const int f_lo = max(0, k * TT - (NT - 1));
+      const uint32_t mis_m = (uint32_t)((g_m + (uint64_t)((int64_t)f_lo * ldb_m)) & 15);
+      const uint32_t mis_v = (uint32_t)((g_v + (uint64_t)((int64_t)f_lo * ldb_v)) & 15);
+      const unsigned char* sm_m = ring + (size_t)s * 2 * g.sb_in + mis_m;
+      const unsigned char* sm_v = ring + (size_t)s * 2 * g.sb_in + g.sb_in + mis_v;
+      if (m_edge > 0 && k * TT - (NT - 1) >= m_edge && k * TT + TT <= T - m_edge) do_tile(FullTile<true>{}, k, sm_m, sm_v, dst);
+      else do_tile(FullTile<false>{}, k, sm_m, sm_v, dst);
+      mbar_arrive(pb_full + ps);  // release: this lane's rows are visible to the solver
+      __syncwarp();
+      if (lane == 0 && k + NSA * NA < npb) issue_in(k + NSA * NA, s);
+      if (++s == NSA) { s = 0; par ^= 1; }
+    }
+    return;
+  }
+
+  // ================================= solver warp ========================================================
+  double* const ws0 = p.ws + (size_t)item * ((size_t)p.max_T * NT * 32);
+  double* wsp = ws0 + lane;
+  double vcol[S + 1][S + 1], lcol[S + 1][S + 1], zz[S + 1];
+#pragma unroll
+  for (int k = 0; k <= S; ++k) {
+    zz[k] = 0.0;
+#pragma unroll
+    for (int j = 0; j <= S; ++j) { vcol[k][j] = 0.0; lcol[k][j] = 0.0; }
+  }
+  double iv1 = 0.0;
+  int bad = 0;
+
+  auto eliminate = [&](int t, const double* row) {
+    double acc[S + 1];
+#pragma unroll
+    for (int m = 0; m <= S; ++m) acc[m] = row[m * 32];
+    double bb = row[(S + 1) * 32];
+#pragma unroll
+    for (int k = 2; k <= S; ++k) {
+#pragma unroll
+      for (int m = 0; m + k <= S; ++m) acc[m] = fma(-vcol[k][k + m], lcol[k][k], acc[m]);
+      bb = fma(-lcol[k][k], zz[k], bb);
+    }
+    if (S >= 1) {
+#pragma unroll
+      for (int m = 0; m + 1 <= S; ++m) acc[m] = fma(-(vcol[1][1 + m] * vcol[1][1]), iv1, acc[m]);
+      bb = fma(-(vcol[1][1] * zz[1]), iv1, bb);
+    }
+    const double d = acc[0];
+    bad = (bad == 0 && !(d > 0.0)) ? t + 1 : bad;  // linalg.pyx:79-82
+    const double ivd = rcp_pos(d);
+    wsp[0] = bb * ivd;
+#pragma unroll
+    for (int k = S; k >= 2; --k) {
+      zz[k] = zz[k - 1];
+#pragma unroll
+      for (int j = k; j <= S; ++j) { vcol[k][j] = vcol[k - 1][j]; lcol[k][j] = lcol[k - 1][j]; }
+    }
+    if (S >= 1) {
+      zz[1] = bb;
+#pragma unroll
+      for (int j = 1; j <= S; ++j) {
+        vcol[1][j] = acc[j];
+        const double lj = acc[j] * ivd;
+        lcol[1][j] = lj;
+        wsp[j * 32] = lj;
+      }
+      iv1 = ivd;
+    }
+    wsp += NT * 32;
+  };
+
+  {
+    int ps = 0;
+    uint32_t ppar = 0;
+    for (int k = 0; k < npb; ++k) {
+      mbar_wait(pb_full + ps, ppar);
+      const double* src = pb + (size_t)ps * (TT * NR * 32) + lane;
+      const int r0 = k * TT - L;  // row of the first band row in this tile
+      if (r0 >= 0 && r0 + TT <= T) {
+#pragma unroll
+        for (int j = 0; j < TT; ++j) eliminate(r0 + j, src + (size_t)j * (NR * 32));
+      } else {
+#pragma unroll
+        for (int j = 0; j < TT; ++j)
+          if (r0 + j >= 0 && r0 + j < T) eliminate(r0 + j, src + (size_t)j * (NR * 32));
+      }
+      mbar_arrive(pb_empty + ps);
+      if (++ps == ND) { ps = 0; ppar ^= 1; }
+    }
+  }
+  if (bad && solve) report_not_pd(p.status, utt, chain, bad);
+
+  // ---- backward sweep (solver warp): y[t] = zs[t] - sum_j l_j[t] y[t+j] ---------------------------
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+  unsigned char* ring = rings;  // every assembler has retired: reuse ring 0
+  const int nbt = (T + TTB - 1) / TTB;
+  auto issue_ws = [&](int kb, int s) {
+    const int t0 = (nbt - 1 - kb) * TTB;
+    const uint32_t nb = (uint32_t)(min(T, t0 + TTB) - t0) * NT * 32 * 8;
+    mbar_expect_tx(ws_full + s, nb);
+    bulk_g2s(ring + (size_t)s * g.sb_ws, ws0 + (size_t)t0 * (NT * 32), nb, ws_full + s);
+  };
+  if (lane == 0)
+    for (int kb = 0; kb < NSB && kb < nbt; ++kb) issue_ws(kb, kb);
+  double yw[S + 1];
+#pragma unroll
+  for (int j = 0; j <= S; ++j) yw[j] = 0.0;
+  // output pointer walks backwards with the sweep; lanes that do not own a chain store nothing
+  const int64_t ostep = p.out_ld;
+  Tin* op = outp + (int64_t)(T - 1) * ostep;
+  auto back = [&](const double* fr) {
+#pragma unroll
+    for (int j = S; j > 0; --j) yw[j] = yw[j - 1];
+    // oldest terms first: only the last FMA (with y[t+1]) sits on the loop-carried chain
+    double y = fr[0];
+#pragma unroll
+    for (int j = S; j >= 1; --j) y = fma(-fr[j * 32], yw[j], y);
+    yw[0] = y;
+    st_stream_if(op, (Tin)y, solve);
+    op -= ostep;
+  };
+  {
+    int s = 0;
+    uint32_t par = 0;
+    for (int kb = 0; kb < nbt; ++kb) {
+      mbar_wait(ws_full + s, par);
+      const int t0 = (nbt - 1 - kb) * TTB;
+      const double* smw = reinterpret_cast<const double*>(ring + (size_t)s * g.sb_ws) + lane;
+      if (t0 + TTB <= T) {
+#pragma unroll
+        for (int j = TTB - 1; j >= 0; --j) back(smw + j * (NT * 32));
+      } else {
+        for (int t = T - 1; t >= t0; --t) back(smw + (t - t0) * (NT * 32));
+      }
+      __syncwarp();
+      if (lane == 0 && kb + NSB < nbt) issue_ws(kb + NSB, s);
+      if (++s == NSB) { s = 0; par ^= 1; }
+    }
+  }
+}
+
+template <int TT, int NA, int NSA, int ND, int TTB, int NSB>
+static inline bool as_geometry(int64_t in_ld, int64_t var_ld, int es, int nt, AsGeom& g, size_t& smem_bytes) {
+  const int64_t ld = in_ld > var_ld ? in_ld : var_ld;
+  const size_t sb_in = ((size_t)(TT + nt - 1) * (size_t)ld * es + 32 + 15) / 16 * 16;
+  const size_t sb_ws = (size_t)TTB * nt * 32 * 8;
+  size_t ring_a = ((size_t)NSA * 2 * sb_in + 127) / 128 * 128;
+  const size_t bwd = (size_t)NSB * sb_ws;
+  if ((size_t)NA * ring_a < bwd) ring_a = (bwd / NA + 127) / 128 * 128;
+  const size_t pbb = (size_t)ND * TT * (nt + 1) * 32 * 8;
+  const size_t tot = 512 + (size_t)NA * ring_a + pbb;
+  if (tot > (size_t)100 * 1024) return false;
+  g.sb_in = (uint32_t)sb_in;
+  g.sb_ws = (uint32_t)sb_ws;
+  g.ring_a = (uint32_t)ring_a;
+  g.off_pb = (uint32_t)(512 + (size_t)NA * ring_a);
+  smem_bytes = tot;
+  return true;
+}
+
+}  // namespace nnk

@@ -41,6 +41,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: a warp that expects to wait long (a producer blocked on a full
+// ring) parks instead of polling and stealing issue slots from the warp it is waiting for
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+  for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+    if (mbar_try_wait_hint(bar, parity, 2000u)) return;
+    __nanosleep(200);
+  }
+  __trap();
+}
 // bounded spin: a lost transaction must become an error, never a hung GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
