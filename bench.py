@@ -100,6 +100,10 @@ def cpu_reference(lens, means, variances, n_sample, repeats, cores):
     off = np.concatenate([[0], np.cumsum(lens)])
     items = list(range(n_sample))
     frames = int(off[n_sample])
+    # the reference is single-threaded by construction (.github/workflows/ci.yaml:17 pins OMP_NUM_THREADS=1);
+    # one process per core, no BLAS/OpenMP thread pools inside the workers (the env is inherited on spawn)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[var] = "1"
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores, initializer=_ref_worker_init) as pool:
         pool.map(_ref_one, items[: max(cores, 8)])  # warm-up (imports, page-in)
@@ -354,8 +358,9 @@ def run_ours(args):
                 "api": "nnmnkwii_b200.paramgen.mlpg_batch(numpy pinned) -> nnk_mlpg_batch_host"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "mlpg_kernel<float,3,1,1,FWD> (register prefetch)" if os.environ.get("NNK_MLPG_DIRECT") == "1"
-                     else "mlpg_fwd_tma_kernel<float,3,1,1>",
+                     "traffic": None, "peak_source": peak_src, "kernel": ("mlpg_kernel<float,3,1,1,FWD> (register prefetch)" if os.environ.get("NNK_MLPG_DIRECT") == "1" else
+                                "mlpg_fwd_tma_kernel<float,3,1,1,STD> (single warp)" if os.environ.get("NNK_MLPG_SINGLE") == "1" else
+                                "mlpg_fwd_as_kernel<float,3,1,1,STD> (2 assembler warps + 1 solver warp per 32 chains)"),
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * n_rows},
         "cpu_baseline": cpu_base,
         "clocks": clocks,
@@ -424,9 +429,24 @@ def bench_extras(device, reps=5):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     out["unit_variance_mlpg_fwd_bwd"] = {"frames_per_sec": B * T / (ms * 1e-3), "ms_per_iter": ms, "batch": B, "T": T,
-                                         "static_dim": sd, "algorithmic_bytes": 122.9e6,
-                                         "hbm_gbs_algorithmic": 122.9e6 / (ms * 1e-3) / 1e9,
-                                         "includes": "stencil fwd + loss (torch) + stencil bwd"}
+                                         "static_dim": sd,
+                                         "includes": "autograd step: stencil fwd + loss (torch) + stencil bwd + Python/launch overhead"}
+    # the two stencil sweeps alone (device time of the C-ABI calls, CUDA events)
+    from nnmnkwii_b200 import _uvmlpg as uv
+    band = uv.band_of(R, device)
+    x = mu.detach()
+    go = torch.randn(B, T, sd, device=device, generator=g)
+    for name, fn in (("fwd", lambda: uv.apply_forward(band, x, False)), ("bwd", lambda: uv.apply_backward(band, go, False, 3 * sd))):
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        out["unit_variance_mlpg_" + name + "_sweep"] = {"ms": ms, "algorithmic_bytes": 61.44e6, "hbm_gbs_algorithmic": 61.44e6 / (ms * 1e-3) / 1e9,
+                                                       "band_half_width": band.K, "toeplitz_rows": (band.toep[1] - band.toep[0]) if band.toep else 0}
     return out
 
 

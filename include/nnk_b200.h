@@ -150,6 +150,12 @@ int nnk_uv_band_profile(const void* R, int32_t dtype, int32_t T, int32_t nw, flo
 int nnk_uv_band_extract(const void* R, int32_t dtype, int32_t T, int32_t nw, int32_t K, void* Rb, void* RbT, void* stream);
 int nnk_uv_apply(const void* table, const void* x, void* y, int32_t dtype, int32_t B, int32_t T, int32_t sd,
                  int32_t nw, int32_t K, int32_t backward, int32_t reshaped, void* stream);
+/* float32 variant exploiting that away from the two ends every row of a window block of R is the
+ * same FIR filter: rows [t_lo, t_hi) use `taps` (HOST pointer, nw x (2K+1) floats, passed to the
+ * kernel through the constant bank), the edge rows use `table` as above.                          */
+int nnk_uv_apply_toeplitz(const void* table, const float* taps, const void* x, void* y, int32_t B, int32_t T,
+                          int32_t sd, int32_t nw, int32_t K, int32_t t_lo, int32_t t_hi, int32_t backward,
+                          int32_t reshaped, void* stream);
 
 /* ---- DTW alignment (preprocessing/alignment.py:9-190) ------------------------------------------
  * Batched replacement of `dist, path = fastdtw(x, y, radius=self.radius, dist=self.dist)`

@@ -16,8 +16,30 @@ BAND_REL_TOL = 2.0 ** -32
 _band_cache = {}
 
 
+# rows whose band differs from the middle row by less than this (relative to max |R|) share its filter
+TOEPLITZ_REL_TOL = 2.0 ** -22
+TOEPLITZ_MIN_ROWS = 64
+
+
 class Band(object):
-    __slots__ = ("Rb", "RbT", "K", "T", "nw", "dtype")
+    __slots__ = ("Rb", "RbT", "K", "T", "nw", "dtype", "toep", "toepT")
+
+
+def _toeplitz_interval(table, peak):
+    """(t_lo, t_hi, taps) of the maximal run of rows around T//2 equal to the middle row (host side,
+    once per R): table is the (T, nw, 2K+1) band table."""
+    import numpy as np
+    tab = table.cpu().numpy()
+    T = tab.shape[0]
+    mid = T // 2
+    ok = np.abs(tab - tab[mid]).reshape(T, -1).max(axis=1) <= peak * TOEPLITZ_REL_TOL
+    lo = mid
+    while lo > 0 and ok[lo - 1]:
+        lo -= 1
+    hi = mid + 1
+    while hi < T and ok[hi]:
+        hi += 1
+    return lo, hi, np.ascontiguousarray(tab[mid], dtype=np.float32)
 
 
 def band_of(R, device):
@@ -47,6 +69,14 @@ def band_of(R, device):
     b.RbT = torch.empty((T, nw, 2 * K + 1), dtype=Rd.dtype, device=device)
     _lib.check(lib.nnk_uv_band_extract(Rd.data_ptr(), code, T, nw, K, b.Rb.data_ptr(), b.RbT.data_ptr(), stream),
                "nnk_uv_band_extract")
+    b.toep = b.toepT = None
+    if Rd.dtype == torch.float32 and nw <= 3 and K <= 64 and T >= TOEPLITZ_MIN_ROWS:
+        lo, hi, taps = _toeplitz_interval(b.Rb, peak)
+        if hi - lo >= TOEPLITZ_MIN_ROWS:
+            b.toep = (lo, hi, taps)
+        lo, hi, taps = _toeplitz_interval(b.RbT, peak)
+        if hi - lo >= TOEPLITZ_MIN_ROWS:
+            b.toepT = (lo, hi, taps)
     if len(_band_cache) > 16:
         _band_cache.clear()
     try:
@@ -70,8 +100,14 @@ def apply_forward(band, means3, reshaped):
             means3 = means3[..., : nw * sd]
     x = means3.to(band.dtype).contiguous()
     y = torch.empty((B, T, sd), dtype=band.dtype, device=x.device)
-    _lib.check(lib.nnk_uv_apply(band.Rb.data_ptr(), x.data_ptr(), y.data_ptr(), dev.torch_dtype_code(band.dtype),
-                                B, T, sd, nw, band.K, 0, int(reshaped), dev.current_stream_ptr(x.device)), "nnk_uv_apply")
+    if band.toep is not None:
+        lo, hi, taps = band.toep
+        _lib.check(lib.nnk_uv_apply_toeplitz(band.Rb.data_ptr(), taps.ctypes.data, x.data_ptr(), y.data_ptr(), B, T, sd, nw,
+                                             band.K, lo, hi, 0, int(reshaped), dev.current_stream_ptr(x.device)),
+                   "nnk_uv_apply_toeplitz")
+    else:
+        _lib.check(lib.nnk_uv_apply(band.Rb.data_ptr(), x.data_ptr(), y.data_ptr(), dev.torch_dtype_code(band.dtype),
+                                    B, T, sd, nw, band.K, 0, int(reshaped), dev.current_stream_ptr(x.device)), "nnk_uv_apply")
     return y.to(means3.dtype) if y.dtype != means3.dtype else y
 
 
@@ -85,8 +121,14 @@ def apply_backward(band, grad_output3, reshaped, D):
         gx = torch.empty((B, nw * T, sd), dtype=band.dtype, device=g.device)
     else:
         gx = torch.empty((B, T, nw * sd), dtype=band.dtype, device=g.device)
-    _lib.check(lib.nnk_uv_apply(band.RbT.data_ptr(), g.data_ptr(), gx.data_ptr(), dev.torch_dtype_code(band.dtype),
-                                B, T, sd, nw, band.K, 1, int(reshaped), dev.current_stream_ptr(g.device)), "nnk_uv_apply")
+    if band.toepT is not None:
+        lo, hi, taps = band.toepT
+        _lib.check(lib.nnk_uv_apply_toeplitz(band.RbT.data_ptr(), taps.ctypes.data, g.data_ptr(), gx.data_ptr(), B, T, sd, nw,
+                                             band.K, lo, hi, 1, int(reshaped), dev.current_stream_ptr(g.device)),
+                   "nnk_uv_apply_toeplitz")
+    else:
+        _lib.check(lib.nnk_uv_apply(band.RbT.data_ptr(), g.data_ptr(), gx.data_ptr(), dev.torch_dtype_code(band.dtype),
+                                    B, T, sd, nw, band.K, 1, int(reshaped), dev.current_stream_ptr(g.device)), "nnk_uv_apply")
     if not reshaped and nw * sd != D:  # trailing columns the forward ignored get zero gradient
         full = torch.zeros((B, T, D), dtype=band.dtype, device=g.device)
         full[..., : nw * sd] = gx

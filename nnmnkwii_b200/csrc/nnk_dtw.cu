@@ -48,17 +48,21 @@ struct DtwParams {
   double logdb;
 };
 
-// numpy DOUBLE_pairwise_sum order over a[k] = (x[k]-y[k])^2 without materialising a[]
-__device__ __forceinline__ double sq(const double* __restrict__ x, const double* __restrict__ y, int k) {
-  const double z = __dsub_rn(x[k], y[k]);
+// numpy DOUBLE_pairwise_sum order over a[k] = (x[k]-y[k])^2 without materialising a[]; the operands
+// are widened to float64 first (fastdtw: np.asanyarray(x, dtype='float')), which is exact
+template <typename T>
+__device__ __forceinline__ double sq(const T* __restrict__ x, const T* __restrict__ y, int k) {
+  const double z = __dsub_rn((double)x[k], (double)y[k]);
   return __dmul_rn(z, z);  // never contracted into an FMA: numpy multiplies, then adds
 }
-__device__ __forceinline__ double strided8(const double* x, const double* y, int j, int n8) {
+template <typename T>
+__device__ __forceinline__ double strided8(const T* x, const T* y, int j, int n8) {
   double r = sq(x, y, j);
   for (int i = 8; i < n8; i += 8) r = __dadd_rn(r, sq(x, y, i + j));
   return r;
 }
-__device__ double pairwise_block(const double* x, const double* y, int n) {  // n <= 128
+template <typename T>
+__device__ double pairwise_block(const T* x, const T* y, int n) {  // n <= 128
   if (n < 8) {
     double res = -0.0;
     for (int i = 0; i < n; ++i) res = __dadd_rn(res, sq(x, y, i));
@@ -74,27 +78,34 @@ __device__ double pairwise_block(const double* x, const double* y, int n) {  // 
   for (int i = n8; i < n; ++i) res = __dadd_rn(res, sq(x, y, i));
   return res;
 }
-__device__ double pairwise_sumsq(const double* x, const double* y, int n) {
+template <typename T>
+__device__ double pairwise_sumsq(const T* x, const T* y, int n) {
   if (n <= 128) return pairwise_block(x, y, n);
   int n2 = n / 2;
   n2 -= n2 % 8;
   return __dadd_rn(pairwise_sumsq(x, y, n2), pairwise_sumsq(x + n2, y + n2, n - n2));
 }
 
-__device__ __forceinline__ double local_cost(const double* x, const double* y, int D, int kind, double logdb) {
+template <typename T>
+__device__ __forceinline__ double local_cost(const T* x, const T* y, int D, int kind, double logdb) {
   const double r = sqrt(pairwise_sumsq(x, y, D));
   return kind == 1 ? __dmul_rn(logdb, r) : r;
 }
 
-template <int BLOCK>
-__device__ __forceinline__ void block_sync() {
-  if (BLOCK == 32) __syncwarp();
-  else __syncthreads();
+// ---- FastDTW (radius >= 1): one WARP per pair, the whole recursion inside the warp ---------------
+// Frames the wavefront needs are prefetched into two small shared-memory rings (x rows, y rows) with
+// cp.async a fixed number of diagonals ahead, so the cooperative cost evaluation below reads shared
+// memory, never L2.  The rolling DP diagonals are rings as well.  A level whose window is too wide
+// for the rings (width + lookahead > ring size; never the case for small radii) falls back to
+// global-memory frames and global DP diagonals -- same arithmetic, slower.
+constexpr int FD_RC = 32;  // ring capacity in rows (power of two)
+constexpr int FD_PD = 8;   // prefetch distance in diagonals
+
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-// One CTA per pair.  FULL = exact DTW (radius < 0): no window arrays, back-pointers in global.
-template <int BLOCK, bool FULL>
-__global__ void __launch_bounds__(BLOCK) dtw_kernel(const DtwParams p) {
+__global__ void __launch_bounds__(32) fastdtw_kernel(const DtwParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x;
   const int pair = p.order ? p.order[blockIdx.x] : blockIdx.x;
@@ -106,49 +117,53 @@ __global__ void __launch_bounds__(BLOCK) dtw_kernel(const DtwParams p) {
   }
   // ---- shared memory carve-up -------------------------------------------------------------------
   const int mtx = p.max_tx;
-  double* Dbuf = reinterpret_cast<double*>(smem);  // [3][mtx]
-  int* lo = reinterpret_cast<int*>(Dbuf + 3 * (size_t)mtx);
-  int* hi = lo + (FULL ? 0 : mtx);
-  int* off = hi + (FULL ? 0 : mtx);             // [mtx + 1] row offsets into bp (fast mode)
-  int* jmn = off + (FULL ? 0 : mtx + 1);        // [mtx/2 + 1] coarse path extents per coarse row
-  int* jmx = jmn + (FULL ? 0 : mtx / 2 + 1);
-  unsigned char* bp_s = reinterpret_cast<unsigned char*>(jmx + (FULL ? 0 : mtx / 2 + 1));
+  const int DP = (D + 1) & ~1;                                 // ring row stride (doubles)
+  double* Dring = reinterpret_cast<double*>(smem);            // [3][2*FD_RC]
+  double* xring = Dring + 3 * 2 * FD_RC;                      // [FD_RC][DP]
+  double* yring = xring + (size_t)FD_RC * DP;                 // [FD_RC][DP]
+  int* lo = reinterpret_cast<int*>(yring + (size_t)FD_RC * DP);
+  int* hi = lo + mtx;
+  int* off = hi + mtx;             // [mtx + 1] row offsets into bp
+  int* jmn = off + mtx + 1;        // [mtx/2 + 1] coarse path extents per coarse row
+  int* jmx = jmn + mtx / 2 + 1;
+  unsigned char* bp_s = reinterpret_cast<unsigned char*>(jmx + mtx / 2 + 1);
   __shared__ int s_n;
   __shared__ long long s_cells;
 
   unsigned char* wsp = p.ws + (size_t)pair * p.ws_pair_bytes;
   double* xs = reinterpret_cast<double*>(wsp);
   double* ys = xs + p.series_doubles;
-  unsigned char* bp_g = reinterpret_cast<unsigned char*>(ys + p.series_doubles);
+  double* Dglob = ys + p.series_doubles;                                   // [3][mtx] fallback DP diagonals
+  unsigned char* bp_g = reinterpret_cast<unsigned char*>(Dglob + 3 * (size_t)mtx);
 
   // ---- level 0 = the inputs widened to float64 (fastdtw: np.asanyarray(x, dtype='float')) --------
   {
     const int64_t xb = (int64_t)pair * p.x_pair_stride, yb = (int64_t)pair * p.y_pair_stride;
-    for (int e = tid; e < Tx0 * D; e += BLOCK) {
+    for (int e = tid; e < Tx0 * D; e += 32) {
       const int64_t src = xb + (int64_t)(e / D) * p.x_ld + (e % D);
       xs[e] = p.is_f64 ? reinterpret_cast<const double*>(p.X)[src] : (double)reinterpret_cast<const float*>(p.X)[src];
     }
-    for (int e = tid; e < Ty0 * D; e += BLOCK) {
+    for (int e = tid; e < Ty0 * D; e += 32) {
       const int64_t src = yb + (int64_t)(e / D) * p.y_ld + (e % D);
       ys[e] = p.is_f64 ? reinterpret_cast<const double*>(p.Y)[src] : (double)reinterpret_cast<const float*>(p.Y)[src];
     }
   }
   // ---- coarser levels: __reduce_by_half, until one side is shorter than radius + 2 ----------------
   int nlev = 1;
-  if (!FULL) {
+  {
     const int min_time = p.radius + 2;
     int tx = Tx0, ty = Ty0;
     size_t xo = 0, yo = 0;
-    block_sync<BLOCK>();
+    __syncwarp();
     while (tx >= min_time && ty >= min_time) {
       const int hx = tx / 2, hy = ty / 2;
       const double* xin = xs + xo; const double* yin = ys + yo;
       double* xout = xs + xo + (size_t)tx * D; double* yout = ys + yo + (size_t)ty * D;
-      for (int e = tid; e < hx * D; e += BLOCK) {
+      for (int e = tid; e < hx * D; e += 32) {
         const int i = e / D, k = e % D;
         xout[e] = (xin[(size_t)(2 * i) * D + k] + xin[(size_t)(2 * i + 1) * D + k]) / 2;
       }
-      for (int e = tid; e < hy * D; e += BLOCK) {
+      for (int e = tid; e < hy * D; e += 32) {
         const int i = e / D, k = e % D;
         yout[e] = (yin[(size_t)(2 * i) * D + k] + yin[(size_t)(2 * i + 1) * D + k]) / 2;
       }
@@ -156,11 +171,12 @@ __global__ void __launch_bounds__(BLOCK) dtw_kernel(const DtwParams p) {
       tx = hx; ty = hy;
       ++nlev;
       __threadfence_block();
-      block_sync<BLOCK>();
+      __syncwarp();
     }
   }
   if (tid == 0) s_cells = 0;
-  block_sync<BLOCK>();
+  __threadfence_block();
+  __syncwarp();
 
   // ---- levels, coarsest first ---------------------------------------------------------------------
   for (int lev = nlev - 1; lev >= 0; --lev) {
@@ -169,113 +185,373 @@ __global__ void __launch_bounds__(BLOCK) dtw_kernel(const DtwParams p) {
     for (int l = 0; l < lev; ++l) { xo += (size_t)Tx * D; yo += (size_t)Ty * D; Tx /= 2; Ty /= 2; }
     const double* xl = xs + xo;
     const double* yl = ys + yo;
-    bool bp_in_smem = false;
-    if (!FULL) {
-      // window: full rectangle at the coarsest level, else __expand_window of the coarser path
-      if (lev == nlev - 1) {
-        for (int i = tid; i < Tx; i += BLOCK) { lo[i] = 0; hi[i] = Ty; }
-      } else {
-        const int cx = Tx / 2, r = p.radius;  // coarse rows 0..cx-1 all carry path cells
-        for (int i = tid; i < Tx; i += BLOCK) {
-          const int a = i >> 1;
-          int mn = INT_MAX, mx = -1;
-          for (int aa = max(0, a - r); aa <= min(cx - 1, a + r); ++aa) { mn = min(mn, jmn[aa]); mx = max(mx, jmx[aa]); }
-          int l = 2 * (mn - r), h = 2 * (mx + r) + 2;
-          if (mx < 0) { l = 0; h = 0; }
-          lo[i] = max(0, l);
-          hi[i] = min(Ty, h);
-        }
-      }
-      block_sync<BLOCK>();
-      if (tid == 0) {
-        int acc = 0;
-        for (int i = 0; i < Tx; ++i) { off[i] = acc; acc += max(0, hi[i] - lo[i]); }
-        off[Tx] = acc;
-        s_cells += acc;
-      }
-      block_sync<BLOCK>();
-      bp_in_smem = off[Tx] <= p.smem_bp_cap;
-      for (int a = tid; a < Tx; a += BLOCK) { if (a < mtx / 2 + 1) { jmn[a] = INT_MAX; jmx[a] = -1; } }
+    // window: full rectangle at the coarsest level, else __expand_window of the coarser path
+    if (lev == nlev - 1) {
+      for (int i = tid; i < Tx; i += 32) { lo[i] = 0; hi[i] = Ty; }
     } else {
-      if (tid == 0) s_cells += (long long)Tx * Ty;
+      const int cx = Tx / 2, r = p.radius;  // coarse rows 0..cx-1 all carry path cells
+      for (int i = tid; i < Tx; i += 32) {
+        const int a = i >> 1;
+        int mn = INT_MAX, mx = -1;
+        for (int aa = max(0, a - r); aa <= min(cx - 1, a + r); ++aa) { mn = min(mn, jmn[aa]); mx = max(mx, jmx[aa]); }
+        int l = 2 * (mn - r), h = 2 * (mx + r) + 2;
+        if (mx < 0) { l = 0; h = 0; }
+        lo[i] = max(0, l);
+        hi[i] = min(Ty, h);
+      }
     }
+    __syncwarp();
+    int wmax = 0;
+    {  // exclusive prefix sum of the row widths (warp scan, 32 rows per step) + widest row
+      int carry = 0;
+      for (int base = 0; base < Tx; base += 32) {
+        const int i = base + tid;
+        const int wdt = (i < Tx) ? max(0, hi[i] - lo[i]) : 0;
+        wmax = max(wmax, wdt);
+        int incl = wdt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += t;
+        }
+        if (i < Tx) off[i] = carry + incl - wdt;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (tid == 0) { off[Tx] = carry; s_cells += carry; }
+      wmax = __reduce_max_sync(0xffffffffu, wmax);
+    }
+    __syncwarp();
+    const bool bp_in_smem = off[Tx] <= p.smem_bp_cap;
+    for (int a = tid; a < Tx; a += 32) { if (a < mtx / 2 + 1) { jmn[a] = INT_MAX; jmx[a] = -1; } }
     unsigned char* bp = bp_in_smem ? bp_s : bp_g;
-    block_sync<BLOCK>();
+    // rings usable when (active rows on a diagonal <= widest row) + lookahead fit
+    const bool use_ring = (wmax + FD_PD + 2 <= FD_RC);
+    double* Db = use_ring ? Dring : Dglob;
+    const int dstride = use_ring ? 2 * FD_RC : mtx;
+    const int dmask = use_ring ? (2 * FD_RC - 1) : -1;
+    __syncwarp();
 
     // ---- wavefront over anti-diagonals k = i + j -----------------------------------------------
     int imin = 0, imax = -1;
     const int ndiag = Tx + Ty - 1;
-    for (int k = 0; k < ndiag; ++k) {
-      if (FULL) {
-        imin = max(0, k - (Ty - 1));
-        imax = min(Tx - 1, k);
-      } else {
-        while (imax + 1 < Tx && imax + 1 + lo[imax + 1] <= k) ++imax;
-        while (imin < Tx && imin + hi[imin] <= k) ++imin;
-      }
-      double* dk = Dbuf + (size_t)(k % 3) * mtx;
-      const double* d1 = Dbuf + (size_t)((k + 2) % 3) * mtx;  // diagonal k-1
-      const double* d2 = Dbuf + (size_t)((k + 1) % 3) * mtx;  // diagonal k-2
-      for (int i = imin + tid; i <= imax; i += BLOCK) {
-        const int j = k - i;
-        const double dt = local_cost(xl + (size_t)i * D, yl + (size_t)j * D, D, p.cost_kind, p.logdb);
-        bool vu, vl, vd;
-        if (FULL) {
-          vu = i > 0; vl = j > 0; vd = i > 0 && j > 0;
-        } else {
-          vu = i > 0 && j >= lo[i - 1] && j < hi[i - 1];
-          vl = j - 1 >= lo[i];
-          vd = i > 0 && j - 1 >= lo[i - 1] && j - 1 < hi[i - 1];
-        }
-        const double up = (vu ? d1[i - 1] : CUDART_INF) + dt;
-        const double left = (vl ? d1[i] : CUDART_INF) + dt;
-        const double diag = ((i == 0 && j == 0) ? 0.0 : (vd ? d2[i - 1] : CUDART_INF)) + dt;
-        double best = up;
-        unsigned char dir = 0;
-        if (left < best) { best = left; dir = 1; }
-        if (diag < best) { best = diag; dir = 2; }
-        dk[i] = best;
-        const size_t cell = FULL ? (size_t)i * Ty + j : (size_t)(off[i] + j - lo[i]);
-        bp[cell] = dir;
-      }
-      if (!bp_in_smem) __threadfence_block();
-      block_sync<BLOCK>();
+    int xload = 0, yload = 0;  // rows [0, xload) / [0, yload) have been requested
+    auto fetch_rows = [&](int xt, int yt) {  // request rows up to (exclusive) xt / yt, one commit group
+      for (; xload < xt; ++xload)
+        for (int e = tid; e < D; e += 32) cp_async8(xring + (size_t)(xload & (FD_RC - 1)) * DP + e, xl + (size_t)xload * D + e);
+      for (; yload < yt; ++yload)
+        for (int e = tid; e < D; e += 32) cp_async8(yring + (size_t)(yload & (FD_RC - 1)) * DP + e, yl + (size_t)yload * D + e);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (use_ring) {  // prologue: what diagonals 0 .. FD_PD-1 can need
+      fetch_rows(min(Tx, FD_PD + 1), min(Ty, FD_PD + 1));
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
     }
+    for (int k = 0; k < ndiag; ++k) {
+      while (imax + 1 < Tx && imax + 1 + lo[imax + 1] <= k) ++imax;
+      while (imin < Tx && imin + hi[imin] <= k) ++imin;
+      if (use_ring) {
+        // rows needed FD_PD diagonals from now: x <= imax + FD_PD, y <= (k - imin) + FD_PD
+        fetch_rows(min(Tx, imax + FD_PD + 1), min(Ty, k - imin + FD_PD + 1));
+        asm volatile("cp.async.wait_group %0;" ::"n"(FD_PD) : "memory");
+        __syncwarp();
+      }
+      double* dk = Db + (size_t)(k % 3) * dstride;
+      const double* d1 = Db + (size_t)((k + 2) % 3) * dstride;  // diagonal k-1
+      const double* d2 = Db + (size_t)((k + 1) % 3) * dstride;  // diagonal k-2
+      // Windowed diagonals hold a handful of cells, so the warp works on FOUR cells at a time, eight
+      // lanes per cell: lane l of a group accumulates the strided partial sum r_l of numpy's pairwise
+      // reduction (elements l, l+8, l+16, ...), a three-step butterfly combines r_0..r_7 in exactly
+      // numpy's association ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), lane 0 adds the tail.
+      const int ncell = imax - imin + 1;
+      const int grp = tid >> 3, gl = tid & 7;
+      for (int base = 0; base < ncell; base += 4) {
+        const int c = base + grp;
+        const bool valid = c < ncell;
+        const int i = imin + (valid ? c : 0);
+        const int j = k - i;
+        const double* xr = use_ring ? xring + (size_t)(i & (FD_RC - 1)) * DP : xl + (size_t)i * D;
+        const double* yr = use_ring ? yring + (size_t)(j & (FD_RC - 1)) * DP : yl + (size_t)j * D;
+        double dt;
+        if (D >= 8 && D <= 128) {
+          const int n8 = D - (D % 8);
+          double r = strided8(xr, yr, gl, n8);
+          r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+          r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+          r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+          for (int e = n8; e < D; ++e) r = __dadd_rn(r, sq(xr, yr, e));
+          const double rt = sqrt(r);
+          dt = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
+        } else {
+          dt = local_cost(xr, yr, D, p.cost_kind, p.logdb);
+        }
+        if (valid && gl == 0) {
+          const bool vu = i > 0 && j >= lo[i - 1] && j < hi[i - 1];
+          const bool vl = j - 1 >= lo[i];
+          const bool vd = i > 0 && j - 1 >= lo[i - 1] && j - 1 < hi[i - 1];
+          const double up = (vu ? d1[(i - 1) & dmask] : CUDART_INF) + dt;
+          const double left = (vl ? d1[i & dmask] : CUDART_INF) + dt;
+          const double diag = ((i == 0 && j == 0) ? 0.0 : (vd ? d2[(i - 1) & dmask] : CUDART_INF)) + dt;
+          double best = up;
+          unsigned char dir = 0;
+          if (left < best) { best = left; dir = 1; }
+          if (diag < best) { best = diag; dir = 2; }
+          dk[i & dmask] = best;
+          bp[(size_t)(off[i] + j - lo[i])] = dir;
+        }
+      }
+      if (!bp_in_smem || !use_ring) __threadfence_block();  // global back-pointers / diagonals
+      __syncwarp();
+    }
+    if (use_ring) asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     // ---- backtrack (one thread; the path is a dependent chain) --------------------------------------
     if (tid == 0) {
       int i = Tx - 1, j = Ty - 1, n = 0;
       bool ok = true;
-      if (lev == 0) p.dist[pair] = Dbuf[(size_t)((ndiag - 1) % 3) * mtx + (Tx - 1)];
+      if (lev == 0) p.dist[pair] = Db[(size_t)((ndiag - 1) % 3) * dstride + ((Tx - 1) & dmask)];
       int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
       int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
       while (i >= 0 && j >= 0) {
-        if (!FULL && (j < lo[i] || j >= hi[i])) { ok = false; break; }
+        if (j < lo[i] || j >= hi[i]) { ok = false; break; }
         if (lev == 0) {
           if (n >= p.path_ld) { ok = false; break; }
           pi[n] = i; pj[n] = j;
-        } else if (!FULL) {
+        } else {
           jmn[i] = min(jmn[i], j);
           jmx[i] = max(jmx[i], j);
         }
         ++n;
-        const size_t cell = FULL ? (size_t)i * Ty + j : (size_t)(off[i] + j - lo[i]);
-        const unsigned char dir = bp[cell];
+        const unsigned char dir = bp[(size_t)(off[i] + j - lo[i])];
         if (dir == 0) --i;
         else if (dir == 1) --j;
         else { --i; --j; }
-        if (i < 0 || j < 0) break;
       }
       s_n = ok ? n : -1;
     }
-    block_sync<BLOCK>();
+    __threadfence_block();
+    __syncwarp();
   }
   // ---- finalise: reverse the level-0 path in place ------------------------------------------------------
   const int n = s_n;
   if (n > 0) {
     int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
     int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
-    for (int a = tid; a < n / 2; a += BLOCK) {
+    for (int a = tid; a < n / 2; a += 32) {
+      const int b2 = n - 1 - a;
+      const int32_t ti = pi[a], tj = pj[a];
+      pi[a] = pi[b2]; pj[a] = pj[b2];
+      pi[b2] = ti; pj[b2] = tj;
+    }
+  }
+  if (tid == 0) {
+    p.path_len[pair] = n;
+    if (p.cells) p.cells[pair] = s_cells;
+  }
+}
+
+// ---- exact DTW (radius < 0): cost pass + wavefront pass --------------------------------------------
+// The local cost of a cell does not depend on the recurrence, so the exact mode is split in two:
+//   dtw_cost_kernel : one thread per cell, all cells of all pairs in parallel, float64 cost written
+//                     in DIAGONAL-MAJOR order (cell (i, k-i) of diagonal k at diag_off(k) + i - imin(k));
+//   dtw_dp_kernel   : one CTA per pair walks the anti-diagonals; a diagonal's costs and back-pointers
+//                     are contiguous, so every access of the wavefront is coalesced; three rolling
+//                     diagonals of D live in shared memory; thread 0 backtracks at the end.
+// number of cells on diagonals 0 .. k-1 of a Tx x Ty rectangle
+__device__ __forceinline__ long long diag_off(int k, int Tx, int Ty) {
+  const long long a = min(Tx, Ty), b = max(Tx, Ty);
+  if (k <= a) return (long long)k * (k + 1) / 2;
+  if (k <= b) return a * (a + 1) / 2 + (k - a) * a;
+  const long long m = k - b;
+  return a * (a + 1) / 2 + (b - a) * a + m * a - m * (m + 1) / 2;
+}
+
+struct DtwExactParams {
+  const void* X;
+  const void* Y;
+  int n_pairs;           // pairs in this chunk
+  int first;             // rank of the chunk's first pair in `order`
+  int64_t x_pair_stride, y_pair_stride;
+  int x_ld, y_ld, D;
+  const int32_t* len_x;
+  const int32_t* len_y;
+  const int32_t* order;
+  int cost_kind;
+  int32_t* path_i;
+  int32_t* path_j;
+  int path_ld;
+  int32_t* path_len;
+  double* dist;
+  long long* cells;
+  int max_tx, max_ty;
+  double* cost;          // [chunk][max_tx * max_ty]
+  unsigned char* bp;     // [chunk][max_tx * max_ty]
+  double logdb;
+  int chd;               // 256-cell chunks per diagonal
+};
+
+// Tiled cost pass.  A block owns a TI x TJ tile of cells: the TI frames of x and TJ frames of y are
+// staged ONCE in shared memory as float64 (coalesced loads, one conversion per element instead of
+// one per cell); thread t owns row i0 + t and sweeps the tile along anti-diagonals (lane l of a warp
+// is at column j0 + c - l in step c), so the 32 costs a warp produces per step belong to one
+// diagonal and land contiguously in the diagonal-major cost buffer.  Per cell: numpy's pairwise sum
+// with its eight static accumulators, float64, no FMA contraction.
+constexpr int DTW_TI = 128, DTW_TJ = 64;
+
+__device__ __forceinline__ int dtw_row_stride(int D) {  // doubles; even, and stride/2 odd: LDS.128 conflict-free
+  int dp = (D + 1) & ~1;
+  if (((dp >> 1) & 1) == 0) dp += 2;
+  return dp;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(DTW_TI) dtw_cost_kernel(const DtwExactParams p) {
+  extern __shared__ __align__(16) unsigned char smem_c[];
+  const int slot = blockIdx.y;
+  const int pair = p.order ? p.order[p.first + slot] : p.first + slot;
+  const int Tx = p.len_x[pair], Ty = p.len_y[pair];
+  if (Tx <= 0 || Ty <= 0) return;
+  const int tiles_j = (p.max_ty + DTW_TJ - 1) / DTW_TJ;
+  const int i0 = (blockIdx.x / tiles_j) * DTW_TI, j0 = (blockIdx.x % tiles_j) * DTW_TJ;
+  if (i0 >= Tx || j0 >= Ty) return;
+  const int D = p.D, DP = dtw_row_stride(D);
+  double* xs = reinterpret_cast<double*>(smem_c);  // [TI][DP]
+  double* ys = xs + (size_t)DTW_TI * DP;           // [TJ][DP]
+  const int tid = threadIdx.x;
+  const T* X = reinterpret_cast<const T*>(p.X) + (int64_t)pair * p.x_pair_stride;
+  const T* Y = reinterpret_cast<const T*>(p.Y) + (int64_t)pair * p.y_pair_stride;
+  const int ni = min(DTW_TI, Tx - i0), nj = min(DTW_TJ, Ty - j0);
+  for (int e = tid; e < ni * D; e += DTW_TI) {
+    const int r = e / D, k = e - r * D;
+    xs[(size_t)r * DP + k] = (double)X[(int64_t)(i0 + r) * p.x_ld + k];
+  }
+  for (int e = tid; e < nj * D; e += DTW_TI) {
+    const int r = e / D, k = e - r * D;
+    ys[(size_t)r * DP + k] = (double)Y[(int64_t)(j0 + r) * p.y_ld + k];
+  }
+  __syncthreads();
+  const int lane = tid & 31, wbase = tid & ~31;
+  const int i = i0 + tid;
+  const double* xr = xs + (size_t)tid * DP;
+  double* cost = p.cost + (size_t)slot * ((size_t)p.max_tx * p.max_ty);
+  const int nsteps = DTW_TJ + 31;
+  for (int c = 0; c < nsteps; ++c) {
+    const int jl = c - lane;  // column inside the tile
+    const int k = i0 + wbase + j0 + c;  // diagonal of every lane of this warp in this step
+    if (i < Tx && jl >= 0 && jl < nj) {
+      const double* yr = ys + (size_t)jl * DP;
+      double res;
+      if (D < 8) {
+        res = -0.0;
+        for (int e = 0; e < D; ++e) res = __dadd_rn(res, sq(xr, yr, e));
+      } else if (D <= 128) {
+        double r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = sq(xr, yr, q);
+        const int n8 = D - (D % 8);
+        for (int e = 8; e < n8; e += 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) r[q] = __dadd_rn(r[q], sq(xr, yr, e + q));
+        }
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (int e = n8; e < D; ++e) res = __dadd_rn(res, sq(xr, yr, e));
+      } else {
+        res = pairwise_sumsq(xr, yr, D);
+      }
+      const double rt = sqrt(res);
+      const int j = j0 + jl;
+      cost[(size_t)diag_off(k, Tx, Ty) + (i - max(0, k - (Ty - 1)))] = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
+      (void)j;
+    }
+  }
+}
+
+template <int MC>
+__global__ void __launch_bounds__(256) dtw_dp_kernel(const DtwExactParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* Dbuf = reinterpret_cast<double*>(smem);  // [3][max_tx]
+  __shared__ int s_n;
+  const int tid = threadIdx.x;
+  const int slot = blockIdx.x;
+  const int pair = p.order ? p.order[p.first + slot] : p.first + slot;
+  const int Tx = p.len_x[pair], Ty = p.len_y[pair];
+  if (Tx <= 0 || Ty <= 0) {
+    if (tid == 0) { p.path_len[pair] = 0; p.dist[pair] = 0.0; if (p.cells) p.cells[pair] = 0; }
+    return;
+  }
+  const int mtx = p.max_tx;
+  const double* cost = p.cost + (size_t)slot * ((size_t)p.max_tx * p.max_ty);
+  unsigned char* bp = p.bp + (size_t)slot * ((size_t)p.max_tx * p.max_ty);
+  const int ndiag = Tx + Ty - 1;
+  long long off = 0;
+  // the costs of diagonal k+1 are fetched while diagonal k is being relaxed (MC cells per thread)
+  double cnext[MC];
+  {
+    const int imax0 = 0;
+#pragma unroll
+    for (int m = 0; m < MC; ++m) cnext[m] = (tid + 256 * m <= imax0) ? cost[tid + 256 * m] : 0.0;
+  }
+  for (int k = 0; k < ndiag; ++k) {
+    const int imin = max(0, k - (Ty - 1)), imax = min(Tx - 1, k);
+    const int ncur = imax - imin + 1;
+    double ccur[MC];
+#pragma unroll
+    for (int m = 0; m < MC; ++m) ccur[m] = cnext[m];
+    if (k + 1 < ndiag) {
+      const int nmin = max(0, k + 1 - (Ty - 1)), nmax = min(Tx - 1, k + 1);
+      const double* cn = cost + off + ncur;
+#pragma unroll
+      for (int m = 0; m < MC; ++m) cnext[m] = (tid + 256 * m <= nmax - nmin) ? cn[tid + 256 * m] : 0.0;
+    }
+    double* dk = Dbuf + (size_t)(k % 3) * mtx;
+    const double* d1 = Dbuf + (size_t)((k + 2) % 3) * mtx;
+    const double* d2 = Dbuf + (size_t)((k + 1) % 3) * mtx;
+#pragma unroll
+    for (int m = 0; m < MC; ++m) {
+      const int i = imin + tid + 256 * m;
+      if (i <= imax) {
+        const int j = k - i;
+        const double dt = ccur[m];
+        const double up = (i > 0 ? d1[i - 1] : CUDART_INF) + dt;
+        const double left = (j > 0 ? d1[i] : CUDART_INF) + dt;
+        const double diag = ((i == 0 && j == 0) ? 0.0 : ((i > 0 && j > 0) ? d2[i - 1] : CUDART_INF)) + dt;
+        double best = up;
+        unsigned char dir = 0;
+        if (left < best) { best = left; dir = 1; }
+        if (diag < best) { best = diag; dir = 2; }
+        dk[i] = best;
+        bp[off + (i - imin)] = dir;
+      }
+    }
+    off += ncur;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    __threadfence_block();
+    int i = Tx - 1, j = Ty - 1, n = 0;
+    bool ok = true;
+    p.dist[pair] = Dbuf[(size_t)((ndiag - 1) % 3) * mtx + (Tx - 1)];
+    int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
+    int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
+    while (i >= 0 && j >= 0) {
+      if (n >= p.path_ld) { ok = false; break; }
+      pi[n] = i; pj[n] = j;
+      ++n;
+      const int k = i + j;
+      const unsigned char dir = bp[diag_off(k, Tx, Ty) + (i - max(0, k - (Ty - 1)))];
+      if (dir == 0) --i;
+      else if (dir == 1) --j;
+      else { --i; --j; }
+    }
+    s_n = ok ? n : -1;
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > 0) {
+    int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
+    int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
+    for (int a = tid; a < n / 2; a += 256) {
       const int b = n - 1 - a;
       const int32_t ti = pi[a], tj = pj[a];
       pi[a] = pi[b]; pj[a] = pj[b];
@@ -284,8 +560,16 @@ __global__ void __launch_bounds__(BLOCK) dtw_kernel(const DtwParams p) {
   }
   if (tid == 0) {
     p.path_len[pair] = n;
-    if (p.cells) p.cells[pair] = s_cells;
+    if (p.cells) p.cells[pair] = (long long)Tx * Ty;
   }
+}
+
+// pairs per chunk of the exact mode: 9 bytes per cell (float64 cost + back-pointer), <= ~2 GiB per chunk
+static int dtw_exact_chunk(int n_pairs, int max_tx, int max_ty) {
+  const size_t per = (size_t)max_tx * (size_t)max_ty * 9;
+  size_t ch = per ? ((size_t)2 << 30) / per : 1;
+  if (ch < 1) ch = 1;
+  return (int)(ch < (size_t)n_pairs ? ch : (size_t)n_pairs);
 }
 
 // X_aligned[n, :L] = X[n, path[n, :L]]; rows L.. are zero (alignment.py:52-54, 72-73)
@@ -345,9 +629,10 @@ __global__ void trim_len_kernel(const T* __restrict__ X, int64_t pair_stride, in
 
 static size_t dtw_series_doubles(int max_t, int D) { return (size_t)2 * (size_t)max_t * D + 8; }
 
-static size_t dtw_smem_bytes(int max_tx, bool full, int bp_cap) {
-  size_t b = sizeof(double) * 3 * (size_t)max_tx;
-  if (!full) b += sizeof(int) * ((size_t)max_tx * 2 + (max_tx + 1) + 2 * (max_tx / 2 + 1)) + (size_t)bp_cap;
+static size_t dtw_smem_bytes(int max_tx, int D, int bp_cap) {
+  const int dp = (D + 1) & ~1;
+  size_t b = sizeof(double) * (3 * 2 * FD_RC + 2 * (size_t)FD_RC * dp);
+  b += sizeof(int) * ((size_t)max_tx * 2 + (max_tx + 1) + 2 * (max_tx / 2 + 1)) + (size_t)bp_cap;
   return b + 16;
 }
 
@@ -364,9 +649,12 @@ using namespace nnk;
 
 extern "C" size_t nnk_dtw_workspace_bytes(int32_t n_pairs, int32_t max_tx, int32_t max_ty, int32_t D, int32_t radius) {
   const int mt = max_tx > max_ty ? max_tx : max_ty;
-  size_t per = 2 * dtw_series_doubles(mt, D) * sizeof(double);
-  if (radius < 0) per += (size_t)max_tx * (size_t)max_ty;
-  else per += (size_t)max_tx * (size_t)max_ty < ((size_t)64 << 20) ? (size_t)max_tx * (size_t)max_ty : ((size_t)64 << 20);
+  if (radius < 0) {  // exact: chunked float64 cost matrix + back-pointers, diagonal-major
+    const size_t ch = (size_t)dtw_exact_chunk(n_pairs, max_tx, max_ty);
+    return ((ch * (size_t)max_tx * (size_t)max_ty * 9 + 255) / 256 * 256) + 256;
+  }
+  size_t per = 2 * dtw_series_doubles(mt, D) * sizeof(double) + 3 * (size_t)max_tx * sizeof(double);
+  per += (size_t)max_tx * (size_t)max_ty < ((size_t)64 << 20) ? (size_t)max_tx * (size_t)max_ty : ((size_t)64 << 20);
   per = (per + 255) / 256 * 256;
   return per * (size_t)n_pairs;
 }
@@ -395,31 +683,65 @@ extern "C" int nnk_dtw_align(const nnk_dtw_args_t* a, void* stream) {
   const size_t need = nnk_dtw_workspace_bytes(a->n_pairs, a->max_tx, a->max_ty, a->D, a->radius);
   NNK_REQUIRE(a->workspace_bytes >= need, NNK_ERR_WORKSPACE, "DTW workspace too small");
   p.ws_pair_bytes = need / (size_t)a->n_pairs;
-  p.bp_bytes = p.ws_pair_bytes - 2 * p.series_doubles * sizeof(double);
+  p.bp_bytes = 0;
   p.logdb = 10.0 / log(10.0) * sqrt(2.0);  // metrics/__init__.py:5
   int dev = 0, max_smem = 0;
   NNK_CUDA_CHECK(cudaGetDevice(&dev));
   NNK_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   if (full) {
-    constexpr int BLOCK = 256;
-    const size_t smem = dtw_smem_bytes(a->max_tx, true, 0);
+    const size_t smem = sizeof(double) * 3 * (size_t)a->max_tx + 16;
     NNK_REQUIRE(smem <= (size_t)max_smem, NNK_ERR_UNSUPPORTED, "sequence too long for the wavefront buffers in shared memory");
-    p.smem_bp_cap = 0;
-    NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_kernel<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dtw_kernel<BLOCK, true><<<a->n_pairs, BLOCK, smem, st>>>(p);
+    NNK_REQUIRE(a->max_tx <= 256 * 16, NNK_ERR_UNSUPPORTED, "exact DTW supports up to 4096 frames");
+    const int mc = (a->max_tx + 255) / 256;
+    NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_dp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_dp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_dp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ch = dtw_exact_chunk(a->n_pairs, a->max_tx, a->max_ty);
+    const size_t cells = (size_t)a->max_tx * (size_t)a->max_ty;
+    DtwExactParams q;
+    q.X = a->X; q.Y = a->Y; q.x_pair_stride = a->x_pair_stride; q.y_pair_stride = a->y_pair_stride;
+    q.x_ld = a->x_ld; q.y_ld = a->y_ld; q.D = a->D; q.len_x = a->len_x; q.len_y = a->len_y; q.order = a->order;
+    q.cost_kind = a->cost_kind; q.path_i = a->path_i; q.path_j = a->path_j; q.path_ld = a->path_ld;
+    q.path_len = a->path_len; q.dist = a->dist; q.cells = (long long*)a->cells; q.max_tx = a->max_tx; q.max_ty = a->max_ty;
+    q.cost = reinterpret_cast<double*>(a->workspace);
+    q.bp = reinterpret_cast<unsigned char*>(a->workspace) + (size_t)ch * cells * sizeof(double);
+    q.logdb = p.logdb;
+    q.chd = 0;
+    for (int first = 0; first < a->n_pairs; first += ch) {
+      q.first = first;
+      q.n_pairs = (a->n_pairs - first < ch) ? a->n_pairs - first : ch;
+      const int tiles_i = (a->max_tx + DTW_TI - 1) / DTW_TI, tiles_j = (a->max_ty + DTW_TJ - 1) / DTW_TJ;
+      dim3 grid((unsigned)(tiles_i * tiles_j), (unsigned)q.n_pairs);
+      int dp = (a->D + 1) & ~1;
+      if (((dp >> 1) & 1) == 0) dp += 2;
+      const size_t csmem = (size_t)(DTW_TI + DTW_TJ) * dp * sizeof(double);
+      NNK_REQUIRE(csmem <= (size_t)max_smem, NNK_ERR_UNSUPPORTED, "feature dimension too large for the cost tiles");
+      if (a->dtype == NNK_F64) {
+        NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_cost_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        dtw_cost_kernel<double><<<grid, DTW_TI, csmem, st>>>(q);
+      } else {
+        NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_cost_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        dtw_cost_kernel<float><<<grid, DTW_TI, csmem, st>>>(q);
+      }
+      if (mc <= 4) dtw_dp_kernel<4><<<q.n_pairs, 256, smem, st>>>(q);
+      else if (mc <= 8) dtw_dp_kernel<8><<<q.n_pairs, 256, smem, st>>>(q);
+      else dtw_dp_kernel<16><<<q.n_pairs, 256, smem, st>>>(q);
+      count_launch(2);
+      NNK_CUDA_CHECK(cudaGetLastError());
+    }
+    return NNK_OK;
   } else {
-    constexpr int BLOCK = 32;
     size_t bound = dtw_fast_cells_bound(a->max_tx, a->max_ty, a->radius);
-    size_t smem = dtw_smem_bytes(a->max_tx, false, (int)bound);
-    if (smem > (size_t)max_smem / 2) {  // keep >= 2 CTAs per SM; overflow back-pointers go to global scratch
-      const size_t base = dtw_smem_bytes(a->max_tx, false, 0);
+    size_t smem = dtw_smem_bytes(a->max_tx, a->D, (int)bound);
+    if (smem > (size_t)max_smem / 4) {  // keep >= 4 CTAs per SM; overflow back-pointers go to global scratch
+      const size_t base = dtw_smem_bytes(a->max_tx, a->D, 0);
       NNK_REQUIRE(base + 1024 <= (size_t)max_smem, NNK_ERR_UNSUPPORTED, "sequence too long for shared memory");
-      bound = ((size_t)max_smem / 2 > base + 1024) ? (size_t)max_smem / 2 - base : 1024;
-      smem = dtw_smem_bytes(a->max_tx, false, (int)bound);
+      bound = ((size_t)max_smem / 4 > base + 1024) ? (size_t)max_smem / 4 - base : 1024;
+      smem = dtw_smem_bytes(a->max_tx, a->D, (int)bound);
     }
     p.smem_bp_cap = (int)bound;
-    NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_kernel<BLOCK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dtw_kernel<BLOCK, false><<<a->n_pairs, BLOCK, smem, st>>>(p);
+    NNK_CUDA_CHECK(cudaFuncSetAttribute(fastdtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fastdtw_kernel<<<a->n_pairs, 32, smem, st>>>(p);
   }
   count_launch();
   NNK_CUDA_CHECK(cudaGetLastError());

@@ -48,9 +48,11 @@ __global__ void uv_extract_kernel(const T* __restrict__ R, int Tn, int nw, int K
 template <typename T, int BB>
 __global__ void __launch_bounds__(128) uv_fwd_kernel(const T* __restrict__ Rb, const T* __restrict__ x,
                                                      T* __restrict__ y, int B, int Tn, int sd, int nw, int K,
-                                                     int reshaped) {
+                                                     int reshaped, int r_lo, int r_hi, int skip_lo, int skip_hi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int t = blockIdx.x * 4 + warp;
+  int t = r_lo + blockIdx.x * 4 + warp;
+  if (t >= skip_lo) t += skip_hi - skip_lo;  // rows [skip_lo, skip_hi) belong to the Toeplitz kernel
+  if (t >= r_hi) return;
   const int d = blockIdx.y * 32 + lane;
   const int b0 = blockIdx.z * BB;
   if (t >= Tn) return;
@@ -80,9 +82,11 @@ __global__ void __launch_bounds__(128) uv_fwd_kernel(const T* __restrict__ Rb, c
 template <typename T, int BB>
 __global__ void __launch_bounds__(128) uv_bwd_kernel(const T* __restrict__ RbT, const T* __restrict__ go,
                                                      T* __restrict__ gx, int B, int Tn, int sd, int nw, int K,
-                                                     int reshaped) {
+                                                     int reshaped, int r_lo, int r_hi, int skip_lo, int skip_hi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int s = blockIdx.x * 4 + warp;
+  int s = r_lo + blockIdx.x * 4 + warp;
+  if (s >= skip_lo) s += skip_hi - skip_lo;
+  if (s >= r_hi) return;
   const int d = blockIdx.y * 32 + lane;
   const int b0 = blockIdx.z * BB;
   if (s >= Tn) return;
@@ -109,16 +113,130 @@ __global__ void __launch_bounds__(128) uv_bwd_kernel(const T* __restrict__ RbT, 
   }
 }
 
+// ---- Toeplitz interior fast path ---------------------------------------------------------------------
+// Away from the two ends R is shift-invariant (rows of each window block are copies of one FIR
+// filter to float32 rounding): rows t in [t_lo, t_hi) share the coefficient table `h`.  The table
+// lives in the kernel parameter (constant bank), every coefficient index is a compile-time
+// constant after unrolling, so the inner loop is FFMA with a constant operand -- no coefficient
+// loads at all.  One thread produces TTU consecutive frames of one (batch item, static dim) and
+// slides over the TTU + 2K input frames it needs, lanes along d (coalesced row segments).
+template <int KK, int NWT>
+struct UvTaps {
+  float h[NWT][2 * KK + 1];
+};
+
+template <int KK, int NWT, int TTU>
+__global__ void __launch_bounds__(128, 3) uv_fwd_toeplitz_kernel(const __grid_constant__ UvTaps<KK, NWT> taps,
+                                                                 const float* __restrict__ x, float* __restrict__ y, int B,
+                                                                 int Tn, int sd, int t_lo, int t_hi, int reshaped) {
+  const int d = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int t0 = t_lo + (blockIdx.x * 4 + (threadIdx.x >> 5)) * TTU;  // warp-uniform
+  const int b = blockIdx.z;
+  if (t0 >= t_hi || d >= sd) return;
+  float acc[TTU];
+#pragma unroll
+  for (int i = 0; i < TTU; ++i) acc[i] = 0.f;
+  const int64_t fstep = reshaped ? (int64_t)sd : (int64_t)NWT * sd;  // elements between consecutive frames
+  const int s0 = t0 - KK;
+#pragma unroll
+  for (int w = 0; w < NWT; ++w) {
+    const float* px = x + (int64_t)b * Tn * NWT * sd + (reshaped ? ((int64_t)w * Tn + s0) * sd + d : ((int64_t)s0 * NWT + w) * sd + d);
+#pragma unroll
+    for (int r = 0; r < TTU + 2 * KK; ++r) {  // frame s0 + r feeds output i with tap j = r - i
+      const int s = s0 + r;
+      const int sc = min(max(s, 0), Tn - 1);  // frames outside [0, T) contribute zero
+      const float ld = __ldg(px + (int64_t)(sc - s0) * fstep);
+      const float v = (s == sc) ? ld : 0.f;
+#pragma unroll
+      for (int i = 0; i < TTU; ++i) {
+        const int j = r - i;
+        if (j >= 0 && j <= 2 * KK) acc[i] = fmaf(taps.h[w][j], v, acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TTU; ++i)
+    if (t0 + i < t_hi) y[((int64_t)b * Tn + t0 + i) * sd + d] = acc[i];
+}
+
+// backward: gx[b, s, w, d] = sum_j hT[w][j] * go[b, s + j - K, d]; one input stream, NWT outputs
+template <int KK, int NWT, int TTU>
+__global__ void __launch_bounds__(128, 3) uv_bwd_toeplitz_kernel(const __grid_constant__ UvTaps<KK, NWT> taps,
+                                                                 const float* __restrict__ go, float* __restrict__ gx, int B,
+                                                                 int Tn, int sd, int t_lo, int t_hi, int reshaped) {
+  const int d = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int s0 = t_lo + (blockIdx.x * 4 + (threadIdx.x >> 5)) * TTU;
+  const int b = blockIdx.z;
+  if (s0 >= t_hi || d >= sd) return;
+  const int r0 = s0 - KK;
+  const float* pg = go + ((int64_t)b * Tn + r0) * sd + d;
+  const int64_t bbase = (int64_t)b * Tn * NWT * sd;
+  float acc[NWT][TTU];
+#pragma unroll
+  for (int w = 0; w < NWT; ++w)
+#pragma unroll
+    for (int i = 0; i < TTU; ++i) acc[w][i] = 0.f;
+#pragma unroll
+  for (int r = 0; r < TTU + 2 * KK; ++r) {
+    const int t = r0 + r;
+    const int tc = min(max(t, 0), Tn - 1);
+    const float ld = __ldg(pg + (int64_t)(tc - r0) * sd);
+    const float v = (t == tc) ? ld : 0.f;
+#pragma unroll
+    for (int i = 0; i < TTU; ++i) {
+      const int j = r - i;
+      if (j >= 0 && j <= 2 * KK) {
+#pragma unroll
+        for (int w = 0; w < NWT; ++w) acc[w][i] = fmaf(taps.h[w][j], v, acc[w][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < NWT; ++w)
+#pragma unroll
+    for (int i = 0; i < TTU; ++i) {
+      const int s = s0 + i;
+      if (s < t_hi) {
+        const int64_t off = reshaped ? ((int64_t)w * Tn + s) * sd + d : ((int64_t)s * NWT + w) * sd + d;
+        gx[bbase + off] = acc[w][i];
+      }
+    }
+}
+
+template <int KK, int NWT>
+static int uv_toeplitz_launch(const float* taps_host, const float* x, float* y, int B, int Tn, int sd, int t_lo, int t_hi,
+                              int backward, int reshaped, cudaStream_t st) {
+  constexpr int TTU = 8;
+  UvTaps<KK, NWT> taps;
+  for (int w = 0; w < NWT; ++w)
+    for (int j = 0; j <= 2 * KK; ++j) taps.h[w][j] = taps_host[w * (2 * KK + 1) + j];
+  const int rows = t_hi - t_lo;
+  dim3 grid((rows + 4 * TTU - 1) / (4 * TTU), (sd + 31) / 32, B);
+  if (backward) uv_bwd_toeplitz_kernel<KK, NWT, TTU><<<grid, 128, 0, st>>>(taps, x, y, B, Tn, sd, t_lo, t_hi, reshaped);
+  else uv_fwd_toeplitz_kernel<KK, NWT, TTU><<<grid, 128, 0, st>>>(taps, x, y, B, Tn, sd, t_lo, t_hi, reshaped);
+  count_launch();
+  NNK_CUDA_CHECK(cudaGetLastError());
+  return NNK_OK;
+}
+
+template <int KK, int NWT>
+static int uv_toeplitz_launch_pad(const float* padded, const float* x, float* y, int B, int Tn, int sd, int t_lo, int t_hi,
+                                  int backward, int reshaped, cudaStream_t st) {
+  return uv_toeplitz_launch<KK, NWT>(padded, x, y, B, Tn, sd, t_lo, t_hi, backward, reshaped, st);
+}
+
 template <typename T>
 static int uv_apply(const void* tab, const void* x, void* y, int B, int Tn, int sd, int nw, int K, int backward,
-                    int reshaped, cudaStream_t st) {
+                    int reshaped, int skip_lo, int skip_hi, cudaStream_t st) {
   constexpr int BB = 4;
-  dim3 grid((Tn + 3) / 4, (sd + 31) / 32, (B + BB - 1) / BB);
+  const int rows = Tn - (skip_hi - skip_lo);
+  if (rows <= 0) return NNK_OK;
+  dim3 grid((rows + 3) / 4, (sd + 31) / 32, (B + BB - 1) / BB);
   if (grid.y > 65535 || grid.z > 65535) { set_error("static_dim or batch too large for one launch"); return NNK_ERR_ARG; }
   if (backward)
-    uv_bwd_kernel<T, BB><<<grid, 128, 0, st>>>((const T*)tab, (const T*)x, (T*)y, B, Tn, sd, nw, K, reshaped);
+    uv_bwd_kernel<T, BB><<<grid, 128, 0, st>>>((const T*)tab, (const T*)x, (T*)y, B, Tn, sd, nw, K, reshaped, 0, Tn, skip_lo, skip_hi);
   else
-    uv_fwd_kernel<T, BB><<<grid, 128, 0, st>>>((const T*)tab, (const T*)x, (T*)y, B, Tn, sd, nw, K, reshaped);
+    uv_fwd_kernel<T, BB><<<grid, 128, 0, st>>>((const T*)tab, (const T*)x, (T*)y, B, Tn, sd, nw, K, reshaped, 0, Tn, skip_lo, skip_hi);
   count_launch();
   NNK_CUDA_CHECK(cudaGetLastError());
   return NNK_OK;
@@ -156,6 +274,45 @@ extern "C" int nnk_uv_apply(const void* table, const void* x, void* y, int32_t d
   NNK_REQUIRE(B >= 0 && T > 0 && sd >= 0 && nw > 0 && K >= 0, NNK_ERR_ARG, "bad size");
   if (B == 0 || sd == 0) return NNK_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == NNK_F32 ? uv_apply<float>(table, x, y, B, T, sd, nw, K, backward, reshaped, st)
-                          : uv_apply<double>(table, x, y, B, T, sd, nw, K, backward, reshaped, st);
+  return dtype == NNK_F32 ? uv_apply<float>(table, x, y, B, T, sd, nw, K, backward, reshaped, 0, 0, st)
+                          : uv_apply<double>(table, x, y, B, T, sd, nw, K, backward, reshaped, 0, 0, st);
+}
+
+// As nnk_uv_apply (float32 only), but rows [t_lo, t_hi) are computed with the shift-invariant filter
+// `taps` (host pointer, nw x (2K+1) floats: the band row of R those rows share); the remaining edge
+// rows use the per-row table.  Supported: nw <= 3, K <= 64 (otherwise NNK_ERR_UNSUPPORTED: call
+// nnk_uv_apply).
+extern "C" int nnk_uv_apply_toeplitz(const void* table, const float* taps, const void* x, void* y, int32_t B, int32_t T,
+                                     int32_t sd, int32_t nw, int32_t K, int32_t t_lo, int32_t t_hi, int32_t backward,
+                                     int32_t reshaped, void* stream) {
+  NNK_REQUIRE(table && taps && x && y, NNK_ERR_ARG, "NULL pointer");
+  NNK_REQUIRE(B >= 0 && T > 0 && sd >= 0 && nw > 0 && K >= 0 && t_lo >= 0 && t_hi <= T && t_lo <= t_hi, NNK_ERR_ARG, "bad size");
+  if (B == 0 || sd == 0) return NNK_OK;
+  NNK_REQUIRE(B <= 65535 && (sd + 31) / 32 <= 65535, NNK_ERR_ARG, "batch or static_dim too large for one launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = uv_apply<float>(table, x, y, B, T, sd, nw, K, backward, reshaped, t_lo, t_hi, st);
+  if (rc || t_hi == t_lo) return rc;
+  // pad the filter to the next instantiated half-width (extra taps are zero)
+  const int KS[] = {8, 16, 24, 32, 48, 64};
+  int KK = -1;
+  for (int k : KS) if (K <= k) { KK = k; break; }
+  NNK_REQUIRE(KK > 0 && nw <= 3, NNK_ERR_UNSUPPORTED, "Toeplitz path supports nw <= 3 and K <= 64");
+  float padded[3 * 129];
+  for (int w = 0; w < 3; ++w)
+    for (int j = 0; j <= 2 * KK; ++j) {
+      const int jj = j - (KK - K);
+      padded[w * (2 * KK + 1) + j] = (w < nw && jj >= 0 && jj <= 2 * K) ? taps[w * (2 * K + 1) + jj] : 0.f;
+    }
+  const float* xf = (const float*)x;
+  float* yf = (float*)y;
+#define NNK_TOEP(KV)                                                                                              \
+  case KV:                                                                                                        \
+    return nw == 1 ? uv_toeplitz_launch<KV, 1>(padded, xf, yf, B, T, sd, t_lo, t_hi, backward, reshaped, st)      \
+         : nw == 2 ? uv_toeplitz_launch_pad<KV, 2>(padded, xf, yf, B, T, sd, t_lo, t_hi, backward, reshaped, st)  \
+                   : uv_toeplitz_launch_pad<KV, 3>(padded, xf, yf, B, T, sd, t_lo, t_hi, backward, reshaped, st);
+  switch (KK) {
+    NNK_TOEP(8) NNK_TOEP(16) NNK_TOEP(24) NNK_TOEP(32) NNK_TOEP(48) NNK_TOEP(64)
+  }
+#undef NNK_TOEP
+  return NNK_ERR_UNSUPPORTED;
 }
