@@ -92,8 +92,24 @@ def _ref_one(u):
     return out.shape[0]
 
 
-def cpu_reference(lens, means, variances, n_sample, repeats, cores):
-    """frames/s of the reference CPU path on `n_sample` utterances of the workload, `cores` processes."""
+def usable_cores():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:  # cgroup v2 CPU quota, if any
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_reference(lens, means, variances, n_sample, repeats, cores=None):
+    """frames/s of the reference CPU path on `n_sample` utterances of the workload.  The reference is
+    single-threaded; it is given one process per core, and because oversubscribed or throttled hosts
+    make "all cores" slower than fewer, a few pool sizes are tried and the fastest is reported."""
     import multiprocessing as mp
     import oracle
     kind = "reference" if oracle.reference_available() else "port"
@@ -105,19 +121,26 @@ def cpu_reference(lens, means, variances, n_sample, repeats, cores):
     for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
         os.environ[var] = "1"
     ctx = mp.get_context("spawn")
-    with ctx.Pool(cores, initializer=_ref_worker_init) as pool:
-        pool.map(_ref_one, items[: max(cores, 8)])  # warm-up (imports, page-in)
-        best = float("inf")
-        times = []
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            pool.map(_ref_one, items, chunksize=max(1, n_sample // (cores * 4)))
-            dt = time.perf_counter() - t0
-            times.append(dt)
-            best = min(best, dt)
-    return {"value": frames / best, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d of %d utterances (%d frames), per-utterance per-stream paramgen.mlpg, %d processes, best of %d"
-                      % (n_sample, len(lens), frames, cores, repeats)}, times, frames
+    n_all = usable_cores()
+    sizes = [cores] if cores else sorted({min(n_all, c) for c in (n_all, 64, 32, 16, 8)}, reverse=True)
+    best = None
+    tried = {}
+    for size in sizes:
+        with ctx.Pool(size, initializer=_ref_worker_init) as pool:
+            pool.map(_ref_one, items[: max(size, 8)])  # warm-up (imports, page-in)
+            times = []
+            for _ in range(repeats):
+                t0 = time.perf_counter()
+                pool.map(_ref_one, items, chunksize=max(1, n_sample // (size * 4)))
+                times.append(time.perf_counter() - t0)
+        tried[size] = frames / min(times)
+        if best is None or min(times) < min(best[1]):
+            best = (size, times)
+    size, times = best
+    return {"value": frames / min(times), "unit": UNIT, "cores": size, "kind": kind,
+            "sample": "%d of %d utterances (%d frames), per-utterance per-stream paramgen.mlpg, %d processes (of %d usable "
+                      "cores; pool sizes tried -> frames/s: %s), best of %d"
+                      % (n_sample, len(lens), frames, size, n_all, {k: round(v) for k, v in tried.items()}, repeats)}, times, frames
 
 
 def run_reference(args):
@@ -125,11 +148,12 @@ def run_reference(args):
     if rank != 0:
         return
     lens, means, variances = make_batch(0)
-    cores = os.cpu_count() or 1
     steps, warm = max(1, args.steps), max(0, args.warmup)
     # each step = one bounded sample of the workload (whole batch is ~1.5 CPU-seconds on one core)
     n_sample = N_UTT
-    base, times, frames = cpu_reference(lens, means, variances, n_sample, steps + warm, cores)
+    probe, _, _ = cpu_reference(lens, means, variances, n_sample, 1)          # pick the best pool size
+    base, times, frames = cpu_reference(lens, means, variances, n_sample, steps + warm, probe["cores"])
+    base["sample"] = probe["sample"].rsplit(", best of", 1)[0] + ", %d timed steps" % steps
     timed = times[warm:] if len(times) > warm else times
     total = sum(timed)
     val = frames * len(timed) / total
@@ -220,8 +244,7 @@ def run_ours(args):
     # CPU baseline first (rank 0, before CUDA is touched in this process; spawn-based pool)
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        cpu_base, _, _ = cpu_reference(lens, means, variances, N_UTT, 3, cores)
+        cpu_base, _, _ = cpu_reference(lens, means, variances, N_UTT, 2)
 
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)

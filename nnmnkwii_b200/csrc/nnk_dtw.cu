@@ -19,6 +19,7 @@
 // squared differences are summed in float64 in the exact order of numpy's pairwise add-reduce so
 // that costs, ties and therefore back-track indices are bit-identical to the CPU oracle.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "nnk_common.cuh"
 
@@ -45,6 +46,9 @@ struct DtwParams {
   unsigned char* ws;
   size_t ws_pair_bytes, series_doubles, bp_bytes;
   int smem_bp_cap;  // bytes of back-pointer space available in shared memory (fast mode)
+  size_t cost_cap;  // doubles of per-pair cost buffer (fast mode)
+  unsigned long long* prof;  // optional [8] cycle counters (NNK_DTW_PROF=1): build, window, cost, wavefront, backtrack
+  int debug_skip;   // NNK_DTW_SKIP bitmask for phase timing experiments (1 = cost phase, 2 = wavefront, 4 = backtrack)
   double logdb;
 };
 
@@ -92,22 +96,39 @@ __device__ __forceinline__ double local_cost(const T* x, const T* y, int D, int 
   return kind == 1 ? __dmul_rn(logdb, r) : r;
 }
 
-// ---- FastDTW (radius >= 1): one WARP per pair, the whole recursion inside the warp ---------------
-// Frames the wavefront needs are prefetched into two small shared-memory rings (x rows, y rows) with
-// cp.async a fixed number of diagonals ahead, so the cooperative cost evaluation below reads shared
-// memory, never L2.  The rolling DP diagonals are rings as well.  A level whose window is too wide
-// for the rings (width + lookahead > ring size; never the case for small radii) falls back to
-// global-memory frames and global DP diagonals -- same arithmetic, slower.
-constexpr int FD_RC = 32;  // ring capacity in rows (power of two)
-constexpr int FD_PD = 8;   // prefetch distance in diagonals
+// ---- FastDTW (radius >= 1): one CTA (4 warps) per pair, the whole recursion inside the CTA ---------
+// Per level:   (C) all 128 threads evaluate the local cost of every window cell, eight lanes per
+//                  cell (numpy's pairwise order, see below), into a float64 cost buffer -- this is
+//                  the bulk of the arithmetic and has no dependence on the recurrence;
+//              (D) warp 0 walks the anti-diagonals with ONE LANE PER ACTIVE ROW (row i lives in lane
+//                  i & 31): the three predecessors come from the lane's own registers and from the
+//                  neighbouring lane by shuffle, the cell's cost from a small shared-memory ring that
+//                  cp.async fills FD_PD diagonals ahead, so the serial part of a diagonal is a few
+//                  dozen instructions;
+//              (B) thread 0 backtracks and records the per-row extents the next finer level needs.
+// A level whose rows are wider than the lane / ring budget (never for small radii) runs (D) with the
+// straightforward loop over cells instead.
+constexpr int FD_BLOCK = 128;
+constexpr int FD_PD = 7;       // cost prefetch distance in diagonals (ring of FD_PD + 1 = 8 slots)
+constexpr int FD_MAXW = 24;    // most rows active on one diagonal the lane-per-row path takes (+ FD_PD < 32)
 
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(32) fastdtw_kernel(const DtwParams p) {
+#define FD_TICK(slot)                                                            \
+  do {                                                                           \
+    if (p.prof && tid == 0) {                                                    \
+      const long long now_ = clock64();                                          \
+      atomicAdd(p.prof + (slot), (unsigned long long)(now_ - tick_));            \
+      tick_ = now_;                                                              \
+    }                                                                            \
+  } while (0)
+
+__global__ void __launch_bounds__(FD_BLOCK) fastdtw_kernel(const DtwParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int tid = threadIdx.x;
+  long long tick_ = clock64();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = p.order ? p.order[blockIdx.x] : blockIdx.x;
   const int Tx0 = p.len_x[pair], Ty0 = p.len_y[pair];
   const int D = p.D;
@@ -117,36 +138,38 @@ __global__ void __launch_bounds__(32) fastdtw_kernel(const DtwParams p) {
   }
   // ---- shared memory carve-up -------------------------------------------------------------------
   const int mtx = p.max_tx;
-  const int DP = (D + 1) & ~1;                                 // ring row stride (doubles)
-  double* Dring = reinterpret_cast<double*>(smem);            // [3][2*FD_RC]
-  double* xring = Dring + 3 * 2 * FD_RC;                      // [FD_RC][DP]
-  double* yring = xring + (size_t)FD_RC * DP;                 // [FD_RC][DP]
-  int* lo = reinterpret_cast<int*>(yring + (size_t)FD_RC * DP);
+  double* cring = reinterpret_cast<double*>(smem);            // [FD_PD + 1][32] prefetched costs
+  int* lo = reinterpret_cast<int*>(cring + (FD_PD + 1) * 32);
   int* hi = lo + mtx;
-  int* off = hi + mtx;             // [mtx + 1] row offsets into bp
+  int* off = hi + mtx;             // [mtx + 1] row offsets into bp / cost buffer
   int* jmn = off + mtx + 1;        // [mtx/2 + 1] coarse path extents per coarse row
   int* jmx = jmn + mtx / 2 + 1;
   unsigned char* bp_s = reinterpret_cast<unsigned char*>(jmx + mtx / 2 + 1);
-  __shared__ int s_n;
+  __shared__ int s_n, s_wmax;
   __shared__ long long s_cells;
 
   unsigned char* wsp = p.ws + (size_t)pair * p.ws_pair_bytes;
   double* xs = reinterpret_cast<double*>(wsp);
   double* ys = xs + p.series_doubles;
-  double* Dglob = ys + p.series_doubles;                                   // [3][mtx] fallback DP diagonals
-  unsigned char* bp_g = reinterpret_cast<unsigned char*>(Dglob + 3 * (size_t)mtx);
+  double* Dglob = ys + p.series_doubles;                                   // [3][mtx] DP diagonals of the slow path
+  double* cbuf = Dglob + 3 * (size_t)mtx;                                  // [cost_cap] local costs of one level
+  unsigned char* bp_g = reinterpret_cast<unsigned char*>(cbuf + p.cost_cap);
 
   // ---- level 0 = the inputs widened to float64 (fastdtw: np.asanyarray(x, dtype='float')) --------
   {
     const int64_t xb = (int64_t)pair * p.x_pair_stride, yb = (int64_t)pair * p.y_pair_stride;
-    for (int e = tid; e < Tx0 * D; e += 32) {
-      const int64_t src = xb + (int64_t)(e / D) * p.x_ld + (e % D);
-      xs[e] = p.is_f64 ? reinterpret_cast<const double*>(p.X)[src] : (double)reinterpret_cast<const float*>(p.X)[src];
-    }
-    for (int e = tid; e < Ty0 * D; e += 32) {
-      const int64_t src = yb + (int64_t)(e / D) * p.y_ld + (e % D);
-      ys[e] = p.is_f64 ? reinterpret_cast<const double*>(p.Y)[src] : (double)reinterpret_cast<const float*>(p.Y)[src];
-    }
+#pragma unroll 4
+    for (int r = warp; r < Tx0; r += FD_BLOCK / 32)
+      for (int e = lane; e < D; e += 32) {
+        const int64_t src = xb + (int64_t)r * p.x_ld + e;
+        xs[(size_t)r * D + e] = p.is_f64 ? reinterpret_cast<const double*>(p.X)[src] : (double)reinterpret_cast<const float*>(p.X)[src];
+      }
+#pragma unroll 4
+    for (int r = warp; r < Ty0; r += FD_BLOCK / 32)
+      for (int e = lane; e < D; e += 32) {
+        const int64_t src = yb + (int64_t)r * p.y_ld + e;
+        ys[(size_t)r * D + e] = p.is_f64 ? reinterpret_cast<const double*>(p.Y)[src] : (double)reinterpret_cast<const float*>(p.Y)[src];
+      }
   }
   // ---- coarser levels: __reduce_by_half, until one side is shorter than radius + 2 ----------------
   int nlev = 1;
@@ -154,29 +177,28 @@ __global__ void __launch_bounds__(32) fastdtw_kernel(const DtwParams p) {
     const int min_time = p.radius + 2;
     int tx = Tx0, ty = Ty0;
     size_t xo = 0, yo = 0;
-    __syncwarp();
+    __syncthreads();
     while (tx >= min_time && ty >= min_time) {
       const int hx = tx / 2, hy = ty / 2;
       const double* xin = xs + xo; const double* yin = ys + yo;
       double* xout = xs + xo + (size_t)tx * D; double* yout = ys + yo + (size_t)ty * D;
-      for (int e = tid; e < hx * D; e += 32) {
-        const int i = e / D, k = e % D;
-        xout[e] = (xin[(size_t)(2 * i) * D + k] + xin[(size_t)(2 * i + 1) * D + k]) / 2;
-      }
-      for (int e = tid; e < hy * D; e += 32) {
-        const int i = e / D, k = e % D;
-        yout[e] = (yin[(size_t)(2 * i) * D + k] + yin[(size_t)(2 * i + 1) * D + k]) / 2;
-      }
+#pragma unroll 4
+      for (int r = warp; r < hx; r += FD_BLOCK / 32)
+        for (int e = lane; e < D; e += 32)
+          xout[(size_t)r * D + e] = (xin[(size_t)(2 * r) * D + e] + xin[(size_t)(2 * r + 1) * D + e]) / 2;
+#pragma unroll 4
+      for (int r = warp; r < hy; r += FD_BLOCK / 32)
+        for (int e = lane; e < D; e += 32)
+          yout[(size_t)r * D + e] = (yin[(size_t)(2 * r) * D + e] + yin[(size_t)(2 * r + 1) * D + e]) / 2;
       xo += (size_t)tx * D; yo += (size_t)ty * D;
       tx = hx; ty = hy;
       ++nlev;
-      __threadfence_block();
-      __syncwarp();
+      __syncthreads();
     }
   }
   if (tid == 0) s_cells = 0;
-  __threadfence_block();
-  __syncwarp();
+  __syncthreads();
+  FD_TICK(0);
 
   // ---- levels, coarsest first ---------------------------------------------------------------------
   for (int lev = nlev - 1; lev >= 0; --lev) {
@@ -187,10 +209,10 @@ __global__ void __launch_bounds__(32) fastdtw_kernel(const DtwParams p) {
     const double* yl = ys + yo;
     // window: full rectangle at the coarsest level, else __expand_window of the coarser path
     if (lev == nlev - 1) {
-      for (int i = tid; i < Tx; i += 32) { lo[i] = 0; hi[i] = Ty; }
+      for (int i = tid; i < Tx; i += FD_BLOCK) { lo[i] = 0; hi[i] = Ty; }
     } else {
       const int cx = Tx / 2, r = p.radius;  // coarse rows 0..cx-1 all carry path cells
-      for (int i = tid; i < Tx; i += 32) {
+      for (int i = tid; i < Tx; i += FD_BLOCK) {
         const int a = i >> 1;
         int mn = INT_MAX, mx = -1;
         for (int aa = max(0, a - r); aa <= min(cx - 1, a + r); ++aa) { mn = min(mn, jmn[aa]); mx = max(mx, jmx[aa]); }
@@ -200,119 +222,231 @@ __global__ void __launch_bounds__(32) fastdtw_kernel(const DtwParams p) {
         hi[i] = min(Ty, h);
       }
     }
-    __syncwarp();
-    int wmax = 0;
-    {  // exclusive prefix sum of the row widths (warp scan, 32 rows per step) + widest row
-      int carry = 0;
+    __syncthreads();
+    if (warp == 0) {  // exclusive prefix sum of the row widths (warp scan, 32 rows per step) + widest row
+      int carry = 0, wmax = 0;
       for (int base = 0; base < Tx; base += 32) {
-        const int i = base + tid;
+        const int i = base + lane;
         const int wdt = (i < Tx) ? max(0, hi[i] - lo[i]) : 0;
         wmax = max(wmax, wdt);
         int incl = wdt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (tid >= o) incl += t;
+          if (lane >= o) incl += t;
         }
         if (i < Tx) off[i] = carry + incl - wdt;
         carry += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (tid == 0) { off[Tx] = carry; s_cells += carry; }
       wmax = __reduce_max_sync(0xffffffffu, wmax);
+      if (lane == 0) { off[Tx] = carry; s_cells += carry; s_wmax = 0; }
+      (void)wmax;
     }
-    __syncwarp();
-    const bool bp_in_smem = off[Tx] <= p.smem_bp_cap;
-    for (int a = tid; a < Tx; a += 32) { if (a < mtx / 2 + 1) { jmn[a] = INT_MAX; jmx[a] = -1; } }
+    for (int a = tid; a < Tx; a += FD_BLOCK) { if (a < mtx / 2 + 1) { jmn[a] = INT_MAX; jmx[a] = -1; } }
+    __syncthreads();
+    // exact maximum number of rows active on one diagonal: the span grows only when a row enters
+    // (diagonal k = i + lo[i]); the lowest row still active then is the first r with r + hi[r] > k
+    // (r + hi[r] is increasing), found by binary search -- all rows in parallel.
+    {
+      int smax = 0;
+      for (int i = tid; i < Tx; i += FD_BLOCK) {
+        const int k = i + lo[i];
+        int a = 0, b = i;  // first r in [0, i] with r + hi[r] > k
+        while (a < b) {
+          const int m = (a + b) >> 1;
+          if (m + hi[m] > k) b = m; else a = m + 1;
+        }
+        smax = max(smax, i - a + 1);
+      }
+      smax = __reduce_max_sync(0xffffffffu, smax);
+      if (lane == 0) atomicMax(&s_wmax, smax);
+    }
+    __syncthreads();
+    const int ncells = off[Tx];
+    const bool bp_in_smem = ncells <= p.smem_bp_cap;
+    const bool fast_d = (s_wmax <= FD_MAXW) && ((size_t)ncells <= p.cost_cap);
     unsigned char* bp = bp_in_smem ? bp_s : bp_g;
-    // rings usable when (active rows on a diagonal <= widest row) + lookahead fit
-    const bool use_ring = (wmax + FD_PD + 2 <= FD_RC);
-    double* Db = use_ring ? Dring : Dglob;
-    const int dstride = use_ring ? 2 * FD_RC : mtx;
-    const int dmask = use_ring ? (2 * FD_RC - 1) : -1;
-    __syncwarp();
+    FD_TICK(1);
 
-    // ---- wavefront over anti-diagonals k = i + j -----------------------------------------------
-    int imin = 0, imax = -1;
-    const int ndiag = Tx + Ty - 1;
-    int xload = 0, yload = 0;  // rows [0, xload) / [0, yload) have been requested
-    auto fetch_rows = [&](int xt, int yt) {  // request rows up to (exclusive) xt / yt, one commit group
-      for (; xload < xt; ++xload)
-        for (int e = tid; e < D; e += 32) cp_async8(xring + (size_t)(xload & (FD_RC - 1)) * DP + e, xl + (size_t)xload * D + e);
-      for (; yload < yt; ++yload)
-        for (int e = tid; e < D; e += 32) cp_async8(yring + (size_t)(yload & (FD_RC - 1)) * DP + e, yl + (size_t)yload * D + e);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (use_ring) {  // prologue: what diagonals 0 .. FD_PD-1 can need
-      fetch_rows(min(Tx, FD_PD + 1), min(Ty, FD_PD + 1));
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
+    // ---- (C) local costs of every window cell, eight lanes per cell -------------------------------
+    // lane l of a group accumulates the strided partial sum r_l of numpy's pairwise reduction (elements
+    // l, l+8, l+16, ...); a three-step butterfly combines r_0..r_7 in exactly numpy's association
+    // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); lane 0 adds the tail and takes the square root.
+    if (fast_d && !(p.debug_skip & 1)) {
+      const int grp = tid >> 3, gl = tid & 7;  // 16 groups of 8 lanes
+      const int n8 = D - (D % 8), ntail = D - n8;
+      const bool batched = (D >= 8 && D <= 32);  // <= 4 strided elements per lane: one batch of loads per cell
+      int ci = 0;                                 // row cursor of this group
+      for (int c0 = 0; c0 < ncells; c0 += 2 * (FD_BLOCK / 8)) {
+        // two cells per group per trip so that their loads overlap
+        int ii[2], jj[2], cidx[2];
+        bool val[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = c0 + u * (FD_BLOCK / 8) + grp;
+          val[u] = c < ncells;
+          const int cc = val[u] ? c : ncells - 1;
+          while (off[ci + 1] <= cc) ++ci;
+          ii[u] = ci; jj[u] = lo[ci] + (cc - off[ci]); cidx[u] = c;
+        }
+        if (batched) {
+          double xv[2][4], yv[2][4], xt[2], yt[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const double* xr = xl + (size_t)ii[u] * D;
+            const double* yr = yl + (size_t)jj[u] * D;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int e = gl + 8 * m;
+              xv[u][m] = (e < n8) ? xr[e] : 0.0;
+              yv[u][m] = (e < n8) ? yr[e] : 0.0;
+            }
+            xt[u] = (gl < ntail) ? xr[n8 + gl] : 0.0;  // tail element n8 + gl, fetched by lane gl
+            yt[u] = (gl < ntail) ? yr[n8 + gl] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            double z = __dsub_rn(xv[u][0], yv[u][0]);
+            double r = __dmul_rn(z, z);
+#pragma unroll
+            for (int m = 1; m < 4; ++m)
+              if (gl + 8 * m < n8) { z = __dsub_rn(xv[u][m], yv[u][m]); r = __dadd_rn(r, __dmul_rn(z, z)); }
+            r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+            r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+            r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+            z = __dsub_rn(xt[u], yt[u]);
+            const double at = __dmul_rn(z, z);
+            for (int e = 0; e < ntail; ++e) r = __dadd_rn(r, __shfl_sync(0xffffffffu, at, e, 8));  // tail, in order
+            const double rt = sqrt(r);
+            if (val[u] && gl == 0) cbuf[cidx[u]] = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const double* xr = xl + (size_t)ii[u] * D;
+            const double* yr = yl + (size_t)jj[u] * D;
+            double dt;
+            if (D >= 8 && D <= 128) {
+              double r = strided8(xr, yr, gl, n8);
+              r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+              r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+              r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+              for (int e = n8; e < D; ++e) r = __dadd_rn(r, sq(xr, yr, e));
+              const double rt = sqrt(r);
+              dt = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
+            } else {
+              dt = local_cost(xr, yr, D, p.cost_kind, p.logdb);
+            }
+            if (val[u] && gl == 0) cbuf[cidx[u]] = dt;
+          }
+        }
+      }
+      __threadfence_block();
     }
-    for (int k = 0; k < ndiag; ++k) {
-      while (imax + 1 < Tx && imax + 1 + lo[imax + 1] <= k) ++imax;
-      while (imin < Tx && imin + hi[imin] <= k) ++imin;
-      if (use_ring) {
-        // rows needed FD_PD diagonals from now: x <= imax + FD_PD, y <= (k - imin) + FD_PD
-        fetch_rows(min(Tx, imax + FD_PD + 1), min(Ty, k - imin + FD_PD + 1));
+    __syncthreads();
+
+    FD_TICK(2);
+    const int ndiag = Tx + Ty - 1;
+    if (warp == 0 && fast_d && !(p.debug_skip & 2)) {
+      // ---- (D) wavefront, one lane per active row -------------------------------------------------
+      int imin = 0, imax = -1;
+      int r_lo = 0, r_hi = 0, r_off = 0, p_lo = 0, p_hi = 0;  // my row's window / offset, previous row's window
+      int my_row = -1;
+      double D1 = CUDART_INF, D2 = CUDART_INF;                  // my row on diagonals k-1, k-2
+      auto prefetch = [&](int kk, int base_row) {  // costs of diagonal kk for rows base_row .. base_row+31
+        const int r = base_row + lane;
+        if (kk < ndiag && r < Tx) {
+          const int jj = kk - r;
+          const int l = lo[r], h = hi[r];
+          if (jj >= l && jj < h) cp_async8(cring + (size_t)(kk % (FD_PD + 1)) * 32 + (r & 31), cbuf + off[r] + (jj - l));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      for (int kk = 0; kk < FD_PD; ++kk) prefetch(kk, 0);
+      double dist_last = 0.0;
+      for (int k = 0; k < ndiag; ++k) {
+        while (imax + 1 < Tx && imax + 1 + lo[imax + 1] <= k) ++imax;
+        while (imin < Tx && imin + hi[imin] <= k) ++imin;
+        prefetch(k + FD_PD, imin);
         asm volatile("cp.async.wait_group %0;" ::"n"(FD_PD) : "memory");
         __syncwarp();
-      }
-      double* dk = Db + (size_t)(k % 3) * dstride;
-      const double* d1 = Db + (size_t)((k + 2) % 3) * dstride;  // diagonal k-1
-      const double* d2 = Db + (size_t)((k + 1) % 3) * dstride;  // diagonal k-2
-      // Windowed diagonals hold a handful of cells, so the warp works on FOUR cells at a time, eight
-      // lanes per cell: lane l of a group accumulates the strided partial sum r_l of numpy's pairwise
-      // reduction (elements l, l+8, l+16, ...), a three-step butterfly combines r_0..r_7 in exactly
-      // numpy's association ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), lane 0 adds the tail.
-      const int ncell = imax - imin + 1;
-      const int grp = tid >> 3, gl = tid & 7;
-      for (int base = 0; base < ncell; base += 4) {
-        const int c = base + grp;
-        const bool valid = c < ncell;
-        const int i = imin + (valid ? c : 0);
-        const int j = k - i;
-        const double* xr = use_ring ? xring + (size_t)(i & (FD_RC - 1)) * DP : xl + (size_t)i * D;
-        const double* yr = use_ring ? yring + (size_t)(j & (FD_RC - 1)) * DP : yl + (size_t)j * D;
-        double dt;
-        if (D >= 8 && D <= 128) {
-          const int n8 = D - (D % 8);
-          double r = strided8(xr, yr, gl, n8);
-          r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
-          r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
-          r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
-          for (int e = n8; e < D; ++e) r = __dadd_rn(r, sq(xr, yr, e));
-          const double rt = sqrt(r);
-          dt = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
-        } else {
-          dt = local_cost(xr, yr, D, p.cost_kind, p.logdb);
+        // which row does this lane hold on diagonal k?
+        int i = imin + ((lane - imin) & 31);  // the row in [imin, imin+32) congruent to lane
+        const bool active = i <= imax;
+        if (active && i != my_row) {  // row enters: cache its window (and the previous row's)
+          my_row = i;
+          r_lo = lo[i]; r_hi = hi[i]; r_off = off[i];
+          p_lo = i > 0 ? lo[i - 1] : 0; p_hi = i > 0 ? hi[i - 1] : 0;
+          D1 = CUDART_INF; D2 = CUDART_INF;
         }
-        if (valid && gl == 0) {
-          const bool vu = i > 0 && j >= lo[i - 1] && j < hi[i - 1];
-          const bool vl = j - 1 >= lo[i];
-          const bool vd = i > 0 && j - 1 >= lo[i - 1] && j - 1 < hi[i - 1];
-          const double up = (vu ? d1[(i - 1) & dmask] : CUDART_INF) + dt;
-          const double left = (vl ? d1[i & dmask] : CUDART_INF) + dt;
-          const double diag = ((i == 0 && j == 0) ? 0.0 : (vd ? d2[(i - 1) & dmask] : CUDART_INF)) + dt;
+        const double upv = __shfl_sync(0xffffffffu, D1, (lane + 31) & 31);
+        const double dgv = __shfl_sync(0xffffffffu, D2, (lane + 31) & 31);
+        double newD = CUDART_INF;
+        if (active) {
+          const int j = k - i;
+          const double dt = cring[(size_t)(k % (FD_PD + 1)) * 32 + lane];
+          const bool vu = i > 0 && j >= p_lo && j < p_hi;
+          const bool vl = j - 1 >= r_lo;
+          const bool vd = i > 0 && j - 1 >= p_lo && j - 1 < p_hi;
+          const double up = (vu ? upv : CUDART_INF) + dt;
+          const double left = (vl ? D1 : CUDART_INF) + dt;
+          const double diag = ((i == 0 && j == 0) ? 0.0 : (vd ? dgv : CUDART_INF)) + dt;
           double best = up;
           unsigned char dir = 0;
           if (left < best) { best = left; dir = 1; }
           if (diag < best) { best = diag; dir = 2; }
-          dk[i & dmask] = best;
+          newD = best;
+          bp[(size_t)(r_off + j - r_lo)] = dir;
+          if (i == Tx - 1 && j == Ty - 1) dist_last = best;
+        }
+        D2 = D1;
+        D1 = newD;
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      // the last cell (Tx-1, Ty-1) lives in lane (Tx-1) & 31
+      dist_last = __shfl_sync(0xffffffffu, dist_last, (Tx - 1) & 31);
+      if (lane == 0 && lev == 0) p.dist[pair] = dist_last;
+      __threadfence_block();
+    } else if (warp == 0 && !fast_d) {
+      // ---- slow path: loop over the cells of each diagonal, frames and DP diagonals in global memory ----
+      int imin = 0, imax = -1;
+      for (int k = 0; k < ndiag; ++k) {
+        while (imax + 1 < Tx && imax + 1 + lo[imax + 1] <= k) ++imax;
+        while (imin < Tx && imin + hi[imin] <= k) ++imin;
+        double* dk = Dglob + (size_t)(k % 3) * mtx;
+        const double* d1 = Dglob + (size_t)((k + 2) % 3) * mtx;
+        const double* d2 = Dglob + (size_t)((k + 1) % 3) * mtx;
+        for (int i = imin + lane; i <= imax; i += 32) {
+          const int j = k - i;
+          const double dt = local_cost(xl + (size_t)i * D, yl + (size_t)j * D, D, p.cost_kind, p.logdb);
+          const bool vu = i > 0 && j >= lo[i - 1] && j < hi[i - 1];
+          const bool vl = j - 1 >= lo[i];
+          const bool vd = i > 0 && j - 1 >= lo[i - 1] && j - 1 < hi[i - 1];
+          const double up = (vu ? d1[i - 1] : CUDART_INF) + dt;
+          const double left = (vl ? d1[i] : CUDART_INF) + dt;
+          const double diag = ((i == 0 && j == 0) ? 0.0 : (vd ? d2[i - 1] : CUDART_INF)) + dt;
+          double best = up;
+          unsigned char dir = 0;
+          if (left < best) { best = left; dir = 1; }
+          if (diag < best) { best = diag; dir = 2; }
+          dk[i] = best;
           bp[(size_t)(off[i] + j - lo[i])] = dir;
         }
+        __threadfence_block();
+        __syncwarp();
       }
-      if (!bp_in_smem || !use_ring) __threadfence_block();  // global back-pointers / diagonals
-      __syncwarp();
+      if (lane == 0 && lev == 0) p.dist[pair] = Dglob[(size_t)((ndiag - 1) % 3) * mtx + (Tx - 1)];
     }
-    if (use_ring) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    FD_TICK(3);
 
-    // ---- backtrack (one thread; the path is a dependent chain) --------------------------------------
+    // ---- (B) backtrack (one thread; the path is a dependent chain) ----------------------------------
     if (tid == 0) {
       int i = Tx - 1, j = Ty - 1, n = 0;
       bool ok = true;
-      if (lev == 0) p.dist[pair] = Db[(size_t)((ndiag - 1) % 3) * dstride + ((Tx - 1) & dmask)];
       int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
       int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
-      while (i >= 0 && j >= 0) {
+      while (i >= 0 && j >= 0 && !(p.debug_skip & 4)) {
         if (j < lo[i] || j >= hi[i]) { ok = false; break; }
         if (lev == 0) {
           if (n >= p.path_ld) { ok = false; break; }
@@ -329,18 +463,18 @@ __global__ void __launch_bounds__(32) fastdtw_kernel(const DtwParams p) {
       }
       s_n = ok ? n : -1;
     }
-    __threadfence_block();
-    __syncwarp();
+    __syncthreads();
+    FD_TICK(4);
   }
   // ---- finalise: reverse the level-0 path in place ------------------------------------------------------
   const int n = s_n;
   if (n > 0) {
     int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
     int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
-    for (int a = tid; a < n / 2; a += 32) {
-      const int b2 = n - 1 - a;
-      const int32_t ti = pi[a], tj = pj[a];
-      pi[a] = pi[b2]; pj[a] = pj[b2];
+    for (int a2 = tid; a2 < n / 2; a2 += FD_BLOCK) {
+      const int b2 = n - 1 - a2;
+      const int32_t ti = pi[a2], tj = pj[a2];
+      pi[a2] = pi[b2]; pj[a2] = pj[b2];
       pi[b2] = ti; pj[b2] = tj;
     }
   }
@@ -630,8 +764,8 @@ __global__ void trim_len_kernel(const T* __restrict__ X, int64_t pair_stride, in
 static size_t dtw_series_doubles(int max_t, int D) { return (size_t)2 * (size_t)max_t * D + 8; }
 
 static size_t dtw_smem_bytes(int max_tx, int D, int bp_cap) {
-  const int dp = (D + 1) & ~1;
-  size_t b = sizeof(double) * (3 * 2 * FD_RC + 2 * (size_t)FD_RC * dp);
+  (void)D;
+  size_t b = sizeof(double) * (FD_PD + 1) * 32;
   b += sizeof(int) * ((size_t)max_tx * 2 + (max_tx + 1) + 2 * (max_tx / 2 + 1)) + (size_t)bp_cap;
   return b + 16;
 }
@@ -654,6 +788,7 @@ extern "C" size_t nnk_dtw_workspace_bytes(int32_t n_pairs, int32_t max_tx, int32
     return ((ch * (size_t)max_tx * (size_t)max_ty * 9 + 255) / 256 * 256) + 256;
   }
   size_t per = 2 * dtw_series_doubles(mt, D) * sizeof(double) + 3 * (size_t)max_tx * sizeof(double);
+  per += dtw_fast_cells_bound(max_tx, max_ty, radius) * sizeof(double);  // cost buffer of one level
   per += (size_t)max_tx * (size_t)max_ty < ((size_t)64 << 20) ? (size_t)max_tx * (size_t)max_ty : ((size_t)64 << 20);
   per = (per + 255) / 256 * 256;
   return per * (size_t)n_pairs;
@@ -740,8 +875,24 @@ extern "C" int nnk_dtw_align(const nnk_dtw_args_t* a, void* stream) {
       smem = dtw_smem_bytes(a->max_tx, a->D, (int)bound);
     }
     p.smem_bp_cap = (int)bound;
+    p.cost_cap = dtw_fast_cells_bound(a->max_tx, a->max_ty, a->radius);
+    { const char* e = getenv("NNK_DTW_SKIP"); p.debug_skip = e ? atoi(e) : 0; }
+    static unsigned long long* d_prof = nullptr;
+    p.prof = nullptr;
+    if (getenv("NNK_DTW_PROF")) {
+      if (!d_prof) NNK_CUDA_CHECK(cudaMalloc(&d_prof, 8 * sizeof(unsigned long long)));
+      NNK_CUDA_CHECK(cudaMemsetAsync(d_prof, 0, 8 * sizeof(unsigned long long), st));
+      p.prof = d_prof;
+    }
     NNK_CUDA_CHECK(cudaFuncSetAttribute(fastdtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fastdtw_kernel<<<a->n_pairs, 32, smem, st>>>(p);
+    fastdtw_kernel<<<a->n_pairs, FD_BLOCK, smem, st>>>(p);
+    if (p.prof) {  // debug only: synchronises
+      unsigned long long h[8];
+      NNK_CUDA_CHECK(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, st));
+      NNK_CUDA_CHECK(cudaStreamSynchronize(st));
+      fprintf(stderr, "[nnk fastdtw cycles/pair] build=%llu window=%llu cost=%llu wavefront=%llu backtrack=%llu\n",
+              h[0] / a->n_pairs, h[1] / a->n_pairs, h[2] / a->n_pairs, h[3] / a->n_pairs, h[4] / a->n_pairs);
+    }
   }
   count_launch();
   NNK_CUDA_CHECK(cudaGetLastError());
