@@ -199,6 +199,14 @@ int nnk_gather_rows(const void* X, int32_t dtype, int64_t x_pair_stride, int32_t
 int nnk_trim_lengths(const void* X, int32_t dtype, int64_t pair_stride, int32_t ld, int32_t T, int32_t D, double eps,
                      int32_t n_pairs, int32_t* len, void* stream);
 
+/* ---- delta features (preprocessing/generic.py:229-288) ------------------
+ * out[:, w*D + d] = np.correlate(x[:, d], coef_w, mode="same") per utterance of a flat (sum_T, D)
+ * batch: window centred at len(coef_w) // 2, zeros outside the utterance, float64 arithmetic,
+ * result in the dtype of x.  out has nw*D columns.                                                */
+int nnk_delta_features(const void* x, int32_t dtype, int32_t D, int64_t x_ld, const int64_t* utt_off,
+                       const int32_t* utt_len, int32_t n_utt, int32_t max_T, const nnk_windows_t* win, void* out,
+                       int64_t out_ld, void* stream);
+
 const char* nnk_last_error(void);
 int nnk_abi_version(void);
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches).       */

@@ -93,7 +93,7 @@ EXPORTS = [
     "nnk_abi_version", "nnk_last_error", "nnk_launch_count", "nnk_status_decode",
     "nnk_mlpg_fwd", "nnk_mlpg_grad", "nnk_mlpg_solve", "nnk_mlpg_workspace_bytes", "nnk_mlpg_host", "nnk_mlpg_batch_host",
     "nnk_uv_band_profile", "nnk_uv_band_extract", "nnk_uv_apply", "nnk_uv_apply_toeplitz",
-    "nnk_dtw_align", "nnk_dtw_workspace_bytes", "nnk_gather_rows", "nnk_trim_lengths",
+    "nnk_dtw_align", "nnk_dtw_workspace_bytes", "nnk_gather_rows", "nnk_trim_lengths", "nnk_delta_features",
 ]
 
 
@@ -144,6 +144,8 @@ def _load():
     L.nnk_gather_rows.argtypes = [vp, i32, i64, i32, vp, i32, vp, vp, i64, i32, i32, i32, vp]
     L.nnk_trim_lengths.restype = ctypes.c_int
     L.nnk_trim_lengths.argtypes = [vp, i32, i64, i32, i32, i32, ctypes.c_double, i32, vp, vp]
+    L.nnk_delta_features.restype = ctypes.c_int
+    L.nnk_delta_features.argtypes = [vp, i32, i32, i64, vp, vp, i32, i32, ctypes.POINTER(NnkWindows), vp, i64, vp]
     return L
 
 

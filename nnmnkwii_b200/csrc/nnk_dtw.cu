@@ -538,7 +538,9 @@ __device__ __forceinline__ int dtw_row_stride(int D) {  // doubles; even, and st
   return dp;
 }
 
-template <typename T>
+// NB8 = number of 8-element blocks of the pairwise reduction known at compile time (D in
+// [8*NB8, 8*NB8 + 7]); NB8 == 0 selects the generic run-time loops (D < 8 or D > 63).
+template <typename T, int NB8>
 __global__ void __launch_bounds__(DTW_TI) dtw_cost_kernel(const DtwExactParams p) {
   extern __shared__ __align__(16) unsigned char smem_c[];
   const int slot = blockIdx.y;
@@ -568,14 +570,39 @@ __global__ void __launch_bounds__(DTW_TI) dtw_cost_kernel(const DtwExactParams p
   const int i = i0 + tid;
   const double* xr = xs + (size_t)tid * DP;
   double* cost = p.cost + (size_t)slot * ((size_t)p.max_tx * p.max_ty);
+  // this thread's frame of x stays in registers for the whole tile when the block count is static
+  double xreg[NB8 > 0 ? NB8 * 8 + 8 : 1];
+  if (NB8 > 0) {
+#pragma unroll
+    for (int e = 0; e < NB8 * 8 + 8; ++e) xreg[e] = (e < D) ? xr[e] : 0.0;
+  }
+  const int ntail = D - NB8 * 8;
   const int nsteps = DTW_TJ + 31;
+  const bool row_ok = i < Tx;
   for (int c = 0; c < nsteps; ++c) {
     const int jl = c - lane;  // column inside the tile
     const int k = i0 + wbase + j0 + c;  // diagonal of every lane of this warp in this step
-    if (i < Tx && jl >= 0 && jl < nj) {
+    if (row_ok && jl >= 0 && jl < nj) {
       const double* yr = ys + (size_t)jl * DP;
       double res;
-      if (D < 8) {
+      if (NB8 > 0) {
+        double r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const double z = __dsub_rn(xreg[q], yr[q]); r[q] = __dmul_rn(z, z); }
+#pragma unroll
+        for (int bk = 1; bk < NB8; ++bk) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const double z = __dsub_rn(xreg[bk * 8 + q], yr[bk * 8 + q]);
+            r[q] = __dadd_rn(r[q], __dmul_rn(z, z));
+          }
+        }
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+        for (int e = 0; e < 7; ++e)
+          if (e < ntail) { const double z = __dsub_rn(xreg[NB8 * 8 + e], yr[NB8 * 8 + e]); res = __dadd_rn(res, __dmul_rn(z, z)); }
+      } else if (D < 8) {
         res = -0.0;
         for (int e = 0; e < D; ++e) res = __dadd_rn(res, sq(xr, yr, e));
       } else if (D <= 128) {
@@ -594,9 +621,7 @@ __global__ void __launch_bounds__(DTW_TI) dtw_cost_kernel(const DtwExactParams p
         res = pairwise_sumsq(xr, yr, D);
       }
       const double rt = sqrt(res);
-      const int j = j0 + jl;
       cost[(size_t)diag_off(k, Tx, Ty) + (i - max(0, k - (Ty - 1)))] = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
-      (void)j;
     }
   }
 }
@@ -851,13 +876,20 @@ extern "C" int nnk_dtw_align(const nnk_dtw_args_t* a, void* stream) {
       if (((dp >> 1) & 1) == 0) dp += 2;
       const size_t csmem = (size_t)(DTW_TI + DTW_TJ) * dp * sizeof(double);
       NNK_REQUIRE(csmem <= (size_t)max_smem, NNK_ERR_UNSUPPORTED, "feature dimension too large for the cost tiles");
+      const int nb8 = (a->D >= 8 && a->D < 40) ? a->D / 8 : 0;  // registers hold a frame of up to 39 dims
+#define NNK_COST(TT_, NB_)                                                                                              \
+  do {                                                                                                                  \
+    NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_cost_kernel<TT_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)); \
+    dtw_cost_kernel<TT_, NB_><<<grid, DTW_TI, csmem, st>>>(q);                                                          \
+  } while (0)
       if (a->dtype == NNK_F64) {
-        NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_cost_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-        dtw_cost_kernel<double><<<grid, DTW_TI, csmem, st>>>(q);
+        switch (nb8) { case 1: NNK_COST(double, 1); break; case 2: NNK_COST(double, 2); break; case 3: NNK_COST(double, 3); break;
+                       case 4: NNK_COST(double, 4); break; default: NNK_COST(double, 0); }
       } else {
-        NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_cost_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-        dtw_cost_kernel<float><<<grid, DTW_TI, csmem, st>>>(q);
+        switch (nb8) { case 1: NNK_COST(float, 1); break; case 2: NNK_COST(float, 2); break; case 3: NNK_COST(float, 3); break;
+                       case 4: NNK_COST(float, 4); break; default: NNK_COST(float, 0); }
       }
+#undef NNK_COST
       if (mc <= 4) dtw_dp_kernel<4><<<q.n_pairs, 256, smem, st>>>(q);
       else if (mc <= 8) dtw_dp_kernel<8><<<q.n_pairs, 256, smem, st>>>(q);
       else dtw_dp_kernel<16><<<q.n_pairs, 256, smem, st>>>(q);

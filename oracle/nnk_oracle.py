@@ -16,7 +16,7 @@ _lib = None
 
 __all__ = [
     "build", "lib", "mlpg", "mlpg_grad", "unit_variance_mlpg_matrix", "cost", "dtw", "fastdtw",
-    "expand_window", "melcd", "cholesky_banded_lower", "cho_solve_lower", "cholesky_inv_banded", "trim_zeros_frames_len", "import_reference", "reference_available",
+    "expand_window", "melcd", "delta_features", "cholesky_banded_lower", "cho_solve_lower", "cholesky_inv_banded", "trim_zeros_frames_len", "import_reference", "reference_available",
     "LOGDB_CONST",
 ]
 
@@ -212,6 +212,21 @@ def melcd(X, Y, lengths=None):
         z = x[:length] - y[:length]
         s += np.sqrt((z * z).sum(-1)).sum()
     return LOGDB_CONST * float(s) / float(T)
+
+
+def delta_features(x, windows):
+    """preprocessing.delta_features restated (nnmnkwii/preprocessing/generic.py:229-288):
+    per window and static dim ``np.correlate(x[:, d], window, mode="same")`` into a result of x's dtype."""
+    T, D = x.shape
+    assert len(windows) > 0
+    out = np.empty((T, D * len(windows)), dtype=x.dtype)
+    for idx, w in enumerate(windows):
+        window = w[2] if isinstance(w, tuple) else w
+        y = np.zeros_like(x)
+        for d in range(D):
+            y[:, d] = np.correlate(x[:, d], window, mode="same")
+        out[:, D * idx:D * idx + D] = y
+    return out
 
 
 def trim_zeros_frames_len(x, eps=1e-7):

@@ -115,6 +115,13 @@ def main():
     out["melcd_rows"] = np.array([melcd(a, b) for a, b in zip(xs, ys)])
     out["melcd_2d"] = np.array(melcd(xs, ys))
     out["melcd_len"] = np.array(melcd(xs[None], ys[None], lengths=[4]))
+    # delta_features, straight from the reference
+    from nnmnkwii.preprocessing import delta_features
+    for wi, ws in enumerate(windows_set()):
+        for dt in (np.float32, np.float64):
+            x = rng.standard_normal((9, 3)).astype(dt)
+            out["delta_w%d_%s_x" % (wi, np.dtype(dt).name)] = x
+            out["delta_w%d_%s_y" % (wi, np.dtype(dt).name)] = delta_features(x, ws)
     np.savez_compressed(os.path.join(HERE, "mlpg_reference_golden.npz"), **out)
 
     # DTW (restated oracle; see module docstring)

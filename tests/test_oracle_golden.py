@@ -104,3 +104,16 @@ def test_oracle_vs_live_reference():
                 go = rng.standard_normal((T, 3)).astype(np.float32)
                 assert rel_err(oracle.mlpg_grad(m, v, ws, go), G.mlpg_grad(m, v, ws, go)) < 2e-6
         assert np.abs(G.unit_variance_mlpg_matrix(ws, 21) - oracle.unit_variance_mlpg_matrix(ws, 21)).max() < 1e-7
+
+
+def test_delta_features_oracle(golden):
+    # preprocessing.delta_features, golden straight from the reference
+    for wi, ws in enumerate(windows_set()):
+        for dt in ("float32", "float64"):
+            x = golden["delta_w%d_%s_x" % (wi, dt)]
+            y = oracle.delta_features(x, ws)
+            assert y.dtype == x.dtype and np.array_equal(y, golden["delta_w%d_%s_y" % (wi, dt)])
+    # plain-array windows (non-bandmat form, generic.py:283-287)
+    x = np.random.default_rng(0).random((7, 2))
+    assert np.array_equal(oracle.delta_features(x, [np.array([1.0]), np.array([-0.5, 0.0, 0.5])]),
+                          oracle.delta_features(x, windows_set()[1]))
