@@ -203,6 +203,89 @@ __global__ void __launch_bounds__(128, 3) uv_bwd_toeplitz_kernel(const __grid_co
     }
 }
 
+// ---- packed variants: two adjacent static dims per thread --------------------------------------------
+// Blackwell issues FP32 FMAs two at a time from 64-bit register pairs (fma.rn.f32x2, SASS FFMA2):
+// a thread owns dims (2*dl, 2*dl+1), loads its frames as float2 and keeps the filter taps of one
+// window as (h, h) pairs in registers, so the inner loop is one FFMA2 per two multiply-adds and one
+// 8-byte load per two inputs.  Needs an even static_dim and 8-byte aligned tensors.
+template <int KK, int NWT, int TTU, bool BWD>
+__global__ void __launch_bounds__(128, 3) uv_toeplitz2_kernel(const __grid_constant__ UvTaps<KK, NWT> taps,
+                                                              const float* __restrict__ x, float* __restrict__ y, int B,
+                                                              int Tn, int sd, int t_lo, int t_hi, int reshaped) {
+  const int dl = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int d = 2 * dl;
+  const int t0 = t_lo + (blockIdx.x * 4 + (threadIdx.x >> 5)) * TTU;  // warp-uniform
+  const int b = blockIdx.z;
+  if (t0 >= t_hi || d >= sd) return;
+  const int s0 = t0 - KK;
+  const bool interior = (s0 >= 0) && (t0 + TTU + KK <= Tn);
+  const int64_t nwsd = (int64_t)NWT * sd;
+  // forward: NWT input streams (window side), one output; backward: one input stream, NWT outputs
+  float2 acc[BWD ? NWT : 1][TTU];
+#pragma unroll
+  for (int w = 0; w < (BWD ? NWT : 1); ++w)
+#pragma unroll
+    for (int i = 0; i < TTU; ++i) acc[w][i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < NWT; ++w) {
+    float2 hp[2 * KK + 1];
+#pragma unroll
+    for (int j = 0; j <= 2 * KK; ++j) hp[j] = make_float2(taps.h[w][j], taps.h[w][j]);
+    if (BWD && w > 0) {
+      // the input stream is re-read per window: it is L1 resident, the taps are what fills the registers
+    }
+    const float* px;
+    int64_t fstep;
+    if (!BWD) {
+      px = x + (int64_t)b * Tn * nwsd + (reshaped ? ((int64_t)w * Tn + s0) * sd + d : ((int64_t)s0 * NWT + w) * sd + d);
+      fstep = reshaped ? (int64_t)sd : nwsd;
+    } else {
+      px = x + ((int64_t)b * Tn + s0) * sd + d;
+      fstep = sd;
+    }
+    float2(&a)[TTU] = acc[BWD ? w : 0];
+    if (interior) {
+#pragma unroll
+      for (int r = 0; r < TTU + 2 * KK; ++r) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(px + r * fstep));
+#pragma unroll
+        for (int i = 0; i < TTU; ++i) {
+          const int j = r - i;
+          if (j >= 0 && j <= 2 * KK) a[i] = __ffma2_rn(hp[j], v, a[i]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < TTU + 2 * KK; ++r) {
+        const int s = s0 + r;
+        const int sc = min(max(s, 0), Tn - 1);
+        float2 v = __ldg(reinterpret_cast<const float2*>(px + (int64_t)(sc - s0) * fstep));
+        if (s != sc) v = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < TTU; ++i) {
+          const int j = r - i;
+          if (j >= 0 && j <= 2 * KK) a[i] = __ffma2_rn(hp[j], v, a[i]);
+        }
+      }
+    }
+    if (BWD) {
+#pragma unroll
+      for (int i = 0; i < TTU; ++i) {
+        const int s = t0 + i;
+        if (s < t_hi) {
+          const int64_t off = reshaped ? ((int64_t)w * Tn + s) * sd + d : ((int64_t)s * NWT + w) * sd + d;
+          *reinterpret_cast<float2*>(y + (int64_t)b * Tn * nwsd + off) = a[i];
+        }
+      }
+    }
+  }
+  if (!BWD) {
+#pragma unroll
+    for (int i = 0; i < TTU; ++i)
+      if (t0 + i < t_hi) *reinterpret_cast<float2*>(y + ((int64_t)b * Tn + t0 + i) * sd + d) = acc[0][i];
+  }
+}
+
 template <int KK, int NWT>
 static int uv_toeplitz_launch(const float* taps_host, const float* x, float* y, int B, int Tn, int sd, int t_lo, int t_hi,
                               int backward, int reshaped, cudaStream_t st) {
@@ -211,6 +294,15 @@ static int uv_toeplitz_launch(const float* taps_host, const float* x, float* y, 
   for (int w = 0; w < NWT; ++w)
     for (int j = 0; j <= 2 * KK; ++j) taps.h[w][j] = taps_host[w * (2 * KK + 1) + j];
   const int rows = t_hi - t_lo;
+  const bool packed = (sd % 2 == 0) && (((uintptr_t)x | (uintptr_t)y) % 8 == 0) && KK <= 32;
+  if (packed) {
+    dim3 grid2((rows + 4 * TTU - 1) / (4 * TTU), (sd / 2 + 31) / 32, B);
+    if (backward) uv_toeplitz2_kernel<KK, NWT, TTU, true><<<grid2, 128, 0, st>>>(taps, x, y, B, Tn, sd, t_lo, t_hi, reshaped);
+    else uv_toeplitz2_kernel<KK, NWT, TTU, false><<<grid2, 128, 0, st>>>(taps, x, y, B, Tn, sd, t_lo, t_hi, reshaped);
+    count_launch();
+    NNK_CUDA_CHECK(cudaGetLastError());
+    return NNK_OK;
+  }
   dim3 grid((rows + 4 * TTU - 1) / (4 * TTU), (sd + 31) / 32, B);
   if (backward) uv_bwd_toeplitz_kernel<KK, NWT, TTU><<<grid, 128, 0, st>>>(taps, x, y, B, Tn, sd, t_lo, t_hi, reshaped);
   else uv_fwd_toeplitz_kernel<KK, NWT, TTU><<<grid, 128, 0, st>>>(taps, x, y, B, Tn, sd, t_lo, t_hi, reshaped);
@@ -225,10 +317,9 @@ static int uv_toeplitz_launch_pad(const float* padded, const float* x, float* y,
   return uv_toeplitz_launch<KK, NWT>(padded, x, y, B, Tn, sd, t_lo, t_hi, backward, reshaped, st);
 }
 
-template <typename T>
-static int uv_apply(const void* tab, const void* x, void* y, int B, int Tn, int sd, int nw, int K, int backward,
-                    int reshaped, int skip_lo, int skip_hi, cudaStream_t st) {
-  constexpr int BB = 4;
+template <typename T, int BB>
+static int uv_apply_bb(const void* tab, const void* x, void* y, int B, int Tn, int sd, int nw, int K, int backward,
+                       int reshaped, int skip_lo, int skip_hi, cudaStream_t st) {
   const int rows = Tn - (skip_hi - skip_lo);
   if (rows <= 0) return NNK_OK;
   dim3 grid((rows + 3) / 4, (sd + 31) / 32, (B + BB - 1) / BB);
@@ -240,6 +331,15 @@ static int uv_apply(const void* tab, const void* x, void* y, int B, int Tn, int 
   count_launch();
   NNK_CUDA_CHECK(cudaGetLastError());
   return NNK_OK;
+}
+
+// few rows (the edges next to a Toeplitz interior): one batch item per thread for more parallelism;
+// the whole matrix: four batch items per thread so that a coefficient load feeds four FMAs
+template <typename T>
+static int uv_apply(const void* tab, const void* x, void* y, int B, int Tn, int sd, int nw, int K, int backward,
+                    int reshaped, int skip_lo, int skip_hi, cudaStream_t st) {
+  return (skip_hi > skip_lo) ? uv_apply_bb<T, 1>(tab, x, y, B, Tn, sd, nw, K, backward, reshaped, skip_lo, skip_hi, st)
+                             : uv_apply_bb<T, 4>(tab, x, y, B, Tn, sd, nw, K, backward, reshaped, skip_lo, skip_hi, st);
 }
 
 }  // namespace nnk
