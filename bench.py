@@ -472,6 +472,40 @@ def bench_extras(device, reps=5):
         ms = e0.elapsed_time(e1) / 20
         out["unit_variance_mlpg_" + name + "_sweep"] = {"ms": ms, "algorithmic_bytes": 61.44e6, "hbm_gbs_algorithmic": 61.44e6 / (ms * 1e-3) / 1e9,
                                                        "band_half_width": band.K, "toeplitz_rows": (band.toep[1] - band.toep[0]) if band.toep else 0}
+    # --- MLPG at the north_star shape: T=1000, static_dim=60, 3 windows; fwd and mlpg_grad --------------
+    from nnmnkwii_b200 import _device as dev
+    from nnmnkwii_b200 import _lib
+    B2, T2, sd2 = 256, 1000, 60
+    wc = _lib.make_windows(WINDOWS)
+    chains = dev.chains_on_device(dev.simple_chains(sd2), device)
+    off = torch.arange(B2 + 1, dtype=torch.int64, device=device) * T2
+    m2 = torch.rand(B2 * T2, 3 * sd2, device=device, generator=g)
+    v2 = torch.rand(B2 * T2, 3 * sd2, device=device, generator=g) + 0.1
+    v1 = torch.rand(3 * sd2, device=device, generator=g) + 0.1
+    go2 = torch.randn(B2 * T2, sd2, device=device, generator=g)
+    y2 = torch.zeros(B2 * T2, sd2, device=device)
+    g2 = torch.zeros(B2 * T2, 3 * sd2, device=device)
+
+    def run(mode, var, var_ld, rhs, o, out_ld):
+        return dev.run_mlpg(mode, means=m2, variances=var, rhs=rhs, out=o, offsets=off, lengths=None, order=None,
+                            chains=chains, n_chain=sd2, max_T=T2, windows_c=wc, in_ld=3 * sd2, var_ld=var_ld,
+                            go_ld=sd2, out_ld=out_ld, dtype_code=_lib.NNK_F32, go_f64=0, n_utt=B2, device=device,
+                            check=False)
+    cases = (("mlpg_fwd_T1000_sd60", lambda: run("fwd", v2, 3 * sd2, None, y2, sd2), 28 * sd2),
+             ("mlpg_fwd_T1000_sd60_global_variance", lambda: run("fwd", v1, 0, None, y2, sd2), 16 * sd2),
+             ("mlpg_grad_T1000_sd60", lambda: run("grad", v2, 3 * sd2, go2, g2, 3 * sd2), 28 * sd2))
+    for name, fn, bytes_per_frame in cases:
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"frames_per_sec": B2 * T2 / (ms * 1e-3), "ms": ms, "utterances": B2,
+                     "hbm_gbs_algorithmic": bytes_per_frame * B2 * T2 / (ms * 1e-3) / 1e9}
     return out
 
 

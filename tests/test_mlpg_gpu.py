@@ -229,3 +229,58 @@ def test_cfg2_full_size_properties():
         rhs = sum(Wk.T @ (t[:, k] * mu[a:b, k]) for k, Wk in enumerate(W))
         worst = max(worst, np.abs(P @ yy - rhs).max() / np.abs(rhs).max())
     assert worst < 1e-5  # float32 rounding of y, amplified by ||P||
+
+
+def test_batch_edge_cases():
+    """Empty batch, zero-length utterances inside a batch, utterances shorter than the window
+    support (T = 1, 2), all handled without touching neighbours' rows."""
+    G = _G()
+    ws = windows_set()[2]
+    lay = G.merlin_layout()
+    # empty batch
+    y = G.mlpg_batch(np.zeros((0, 187), np.float32), np.ones((0, 187), np.float32), ws, lengths=[], layout=lay)
+    assert y.shape == (0, 63)
+    # zero-length and very short utterances between normal ones
+    lens = np.array([5, 0, 1, 2, 0, 33, 3, 0])
+    rng = np.random.default_rng(77)
+    n = int(lens.sum())
+    m = rng.random((n, 187), dtype=np.float32)
+    v = rng.random((n, 187), dtype=np.float32) + 0.1
+    y = G.mlpg_batch(m, v, ws, lengths=lens, layout=lay)
+    assert rel_err(y, _oracle_merlin(m, v, ws, lens)) < TOL32
+    # one utterance only, T = 1: the dynamic windows are edge-masked, y = means (static part)
+    y1 = G.mlpg_batch(m[:1], v[:1], ws, lengths=[1], layout=lay)
+    assert np.array_equal(y1[0, :60], m[0, :60])
+
+
+def test_ill_conditioned_variances():
+    """Static variances 1e6 times the delta variances (smooth trajectories, cond(P) ~ 1e7): the
+    float64 LDL^T stays within the north_star tolerance by a wide margin."""
+    G = _G()
+    ws = windows_set()[2]
+    rng = np.random.default_rng(5)
+    T, sd = 700, 40
+    m = rng.standard_normal((T, 3 * sd)).astype(np.float32)
+    v = np.empty((T, 3 * sd), np.float32)
+    v[:, :sd] = 10.0 ** rng.uniform(0, 3, (T, sd))
+    v[:, sd:2 * sd] = 10.0 ** rng.uniform(-4, -3, (T, sd))
+    v[:, 2 * sd:] = 10.0 ** rng.uniform(-5, -3, (T, sd))
+    y = G.mlpg(m, v, ws)
+    ref = oracle.mlpg(m, v, ws)
+    assert rel_err(y, ref) < 1e-5
+    y64 = G.mlpg(m.astype(np.float64), v.astype(np.float64), ws)
+    assert rel_err(y64, oracle.mlpg(m.astype(np.float64), v.astype(np.float64), ws)) < 1e-8
+
+
+def test_ragged_batch_cfg5_shape():
+    """BASELINE.json configs[4] shape at a reduced count: mixed T in [200, 2000], LPT order, waves."""
+    G = _G()
+    ws = windows_set()[2]
+    lay = G.merlin_layout()
+    lens, m, v = _merlin_batch(96, 200, 2000, 4242)
+    y = G.mlpg_batch(m, v, ws, lengths=lens, layout=lay)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for u in (0, 1, int(np.argmax(lens)), int(np.argmin(lens)), 95):
+        a, b = off[u], off[u + 1]
+        assert rel_err(y[a:b], _oracle_merlin(m[a:b], v[a:b], ws, lens[u:u + 1])) < TOL32
+    assert np.array_equal(y[:, 61], m[:, 183])
