@@ -506,6 +506,33 @@ def bench_extras(device, reps=5):
         ms = e0.elapsed_time(e1) / reps
         out[name] = {"frames_per_sec": B2 * T2 / (ms * 1e-3), "ms": ms, "utterances": B2,
                      "hbm_gbs_algorithmic": bytes_per_frame * B2 * T2 / (ms * 1e-3) / 1e9}
+    # --- masked melcd over aligned-output sized batches --------------------------------
+    import ctypes
+    Bm, Tm, Dm = 512, 1600, 25
+    Xm = torch.randn(Bm, Tm, Dm, device=device, generator=g)
+    Ym = torch.randn(Bm, Tm, Dm, device=device, generator=g)
+    lens_m = torch.randint(700, Tm + 1, (Bm,), generator=torch.Generator().manual_seed(5)).to(device=device, dtype=torch.int32)
+    need = int(_lib.lib.nnk_metric_workspace_bytes(Bm))
+    wsm = torch.empty(need, dtype=torch.uint8, device=device)
+    res = torch.zeros(2, dtype=torch.float64, device=device)
+    st = dev.current_stream_ptr(device)
+
+    def melcd_call():
+        _lib.check(_lib.lib.nnk_frame_metric(Xm.data_ptr(), Ym.data_ptr(), _lib.NNK_F32, Bm, Tm, Dm, Tm * Dm, Dm,
+                                             lens_m.data_ptr(), 0, ctypes.c_void_p(res.data_ptr()),
+                                             ctypes.c_void_p(res.data_ptr() + 8), ctypes.c_void_p(wsm.data_ptr()),
+                                             ctypes.c_int64(need), st), "nnk_frame_metric")
+    melcd_call()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        melcd_call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    nbytes = 2 * 4 * Dm * int(lens_m.sum().item())
+    out["masked_melcd"] = {"ms": ms, "frames": int(lens_m.sum().item()), "algorithmic_bytes": nbytes,
+                           "hbm_gbs_algorithmic": nbytes / (ms * 1e-3) / 1e9, "includes": "memset + reduction kernel"}
     return out
 
 

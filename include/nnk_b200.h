@@ -207,6 +207,25 @@ int nnk_delta_features(const void* x, int32_t dtype, int32_t D, int64_t x_ld, co
                        const int32_t* utt_len, int32_t n_utt, int32_t max_T, const nnk_windows_t* win, void* out,
                        int64_t out_ld, void* stream);
 
+/* ---- length-masked objective metrics (metrics/__init__.py:27-190) --------
+ * Padded (B, T, D) batches X, Y (element strides item_stride / frame_stride, D contiguous), lengths
+ * (B) int32 on the device or NULL (all T frames valid).  The kernels deliver the SUM (float64) and the
+ * COUNT of contributing frames; mean / sqrt / dB constant are the caller's scalar finish.
+ *   nnk_frame_metric kind 0: sum of per-frame ||x - y||_2      (melcd,               :59-71)
+ *                    kind 1: sum of (x - y)^2 over frames x D  (mean_squared_error,  :103-110)
+ *   nnk_f0_metric    kind 0: sum of (x - y)^2 over frames with src_vuv + tgt_vuv >= 2; count = voiced
+ *                    kind 1: the same on exp(x), exp(y)        (lf0_mean_squared_error, :141-165)
+ *                    kind 2: sum of (src_vuv != tgt_vuv)       (vuv_error,           :181-190)
+ * Deterministic (fixed-order fold of per-block partials).  workspace >= nnk_metric_workspace_bytes(B). */
+int64_t nnk_metric_workspace_bytes(int32_t B);
+int nnk_frame_metric(const void* X, const void* Y, int32_t dtype, int32_t B, int32_t T, int32_t D,
+                     int64_t item_stride, int64_t frame_stride, const int32_t* lengths, int32_t kind, double* sum_out,
+                     int64_t* count_out, void* workspace, int64_t workspace_bytes, void* stream);
+int nnk_f0_metric(const void* src_f0, const void* src_vuv, const void* tgt_f0, const void* tgt_vuv, int32_t dtype,
+                  int32_t B, int32_t T, int64_t item_stride, int64_t frame_stride, const int32_t* lengths,
+                  int32_t kind, double* sum_out, int64_t* count_out, void* workspace, int64_t workspace_bytes,
+                  void* stream);
+
 const char* nnk_last_error(void);
 int nnk_abi_version(void);
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches).       */

@@ -94,6 +94,7 @@ EXPORTS = [
     "nnk_mlpg_fwd", "nnk_mlpg_grad", "nnk_mlpg_solve", "nnk_mlpg_workspace_bytes", "nnk_mlpg_host", "nnk_mlpg_batch_host",
     "nnk_uv_band_profile", "nnk_uv_band_extract", "nnk_uv_apply", "nnk_uv_apply_toeplitz",
     "nnk_dtw_align", "nnk_dtw_workspace_bytes", "nnk_gather_rows", "nnk_trim_lengths", "nnk_delta_features",
+    "nnk_metric_workspace_bytes", "nnk_frame_metric", "nnk_f0_metric",
 ]
 
 
@@ -146,6 +147,12 @@ def _load():
     L.nnk_trim_lengths.argtypes = [vp, i32, i64, i32, i32, i32, ctypes.c_double, i32, vp, vp]
     L.nnk_delta_features.restype = ctypes.c_int
     L.nnk_delta_features.argtypes = [vp, i32, i32, i64, vp, vp, i32, i32, ctypes.POINTER(NnkWindows), vp, i64, vp]
+    L.nnk_metric_workspace_bytes.restype = i64
+    L.nnk_metric_workspace_bytes.argtypes = [i32]
+    L.nnk_frame_metric.restype = ctypes.c_int
+    L.nnk_frame_metric.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, i64, vp]
+    L.nnk_f0_metric.restype = ctypes.c_int
+    L.nnk_f0_metric.argtypes = [vp, vp, vp, vp, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, i64, vp]
     return L
 
 

@@ -122,6 +122,30 @@ def main():
             x = rng.standard_normal((9, 3)).astype(dt)
             out["delta_w%d_%s_x" % (wi, np.dtype(dt).name)] = x
             out["delta_w%d_%s_y" % (wi, np.dtype(dt).name)] = delta_features(x, ws)
+    # length-masked metrics, straight from the reference
+    from nnmnkwii import metrics as M
+    mr = np.random.default_rng(2024)
+    for dt in (np.float32, np.float64):
+        n = np.dtype(dt).name
+        X = mr.standard_normal((6, 37, 25)).astype(dt)
+        Y = (X + 0.3 * mr.standard_normal((6, 37, 25))).astype(dt)
+        lens = [37, 20, 1, 33, 0, 12]
+        f0a = (5.0 + 0.3 * mr.standard_normal((6, 37))).astype(dt)
+        f0b = (5.0 + 0.3 * mr.standard_normal((6, 37))).astype(dt)
+        va = (mr.random((6, 37)) > 0.3).astype(dt)
+        vb = (mr.random((6, 37)) > 0.3).astype(dt)
+        out["met_%s_X" % n], out["met_%s_Y" % n], out["met_lens"] = X, Y, np.array(lens)
+        out["met_%s_f0a" % n], out["met_%s_f0b" % n], out["met_%s_va" % n], out["met_%s_vb" % n] = f0a, f0b, va, vb
+        out["met_%s_vals" % n] = np.array([
+            M.melcd(X, Y), M.melcd(X, Y, lens), M.melcd(X[0], Y[0]), M.melcd(X[0, 0], Y[0, 0]),
+            M.mean_squared_error(X, Y), M.mean_squared_error(X, Y, lens), M.mean_squared_error(X[0, 0], Y[0, 0]),
+            M.lf0_mean_squared_error(f0a, va, f0b, vb), M.lf0_mean_squared_error(f0a, va, f0b, vb, lens),
+            M.lf0_mean_squared_error(f0a, va, f0b, vb, lens, linear_domain=True),
+            M.lf0_mean_squared_error(f0a[0], va[0], f0b[0], vb[0], linear_domain=True),
+            M.lf0_mean_squared_error(f0a[:, :, None], va[:, :, None], f0b[:, :, None], vb[:, :, None], lens),
+            M.vuv_error(va, vb), M.vuv_error(va, vb, lens), M.vuv_error(va[:, :, None], vb[:, :, None], lens),
+            M.melcd(f0a, f0b, lens), M.mean_squared_error(f0a, f0b, lens),
+        ], dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "mlpg_reference_golden.npz"), **out)
 
     # DTW (restated oracle; see module docstring)
