@@ -12,7 +12,8 @@
 // A group of G = min(32, pow2 >= D) lanes owns a frame, so a warp reads 32/G frames = one contiguous
 // span per load instruction; 4 frames per group are in flight.  Accumulation in float64.  The result
 // is deterministic: every block writes one partial, the last block to finish (ticket) adds the
-// partials in index order.
+// partials in index order and resets the ticket, so a workspace that was zero before its first use
+// stays usable without a memset per call (one launch per metric).
 // HBM bound: 2 * sizeof(T) * D bytes per valid frame (4 scalars per frame for the F0 metrics).
 #include "nnk_common.cuh"
 
@@ -259,7 +260,6 @@ extern "C" int nnk_frame_metric(const void* X, const void* Y, int32_t dtype, int
   p.B = B; p.T = T; p.D = D; p.kind = kind; p.out_sum = sum_out; p.out_cnt = reinterpret_cast<long long*>(count_out);
   const int rc = carve(workspace, workspace_bytes, (int64_t)B + 148 * 8, p);
   if (rc) return rc;
-  NNK_CUDA_CHECK(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), st));
   if (dtype == NNK_F32) dispatch_frame<float>(p, st);
   else dispatch_frame<double>(p, st);
   count_launch();
@@ -290,7 +290,6 @@ extern "C" int nnk_f0_metric(const void* src_f0, const void* src_vuv, const void
   p.chunks = pick_chunks(B, T, MT_BLOCK * MT_UNROLL);
   const int rc = carve(workspace, workspace_bytes, (int64_t)B + 148 * 8, p);
   if (rc) return rc;
-  NNK_CUDA_CHECK(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), st));
   if (dtype == NNK_F32) f0_metric_kernel<float><<<(unsigned)(B * p.chunks), MT_BLOCK, 0, st>>>(p);
   else f0_metric_kernel<double><<<(unsigned)(B * p.chunks), MT_BLOCK, 0, st>>>(p);
   count_launch();

@@ -361,10 +361,15 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   constexpr int TTB_AS = 8, NSB_AS = 4;  // backward-sweep scratch ring of the paired kernel: 32 frames in flight
   AsGeom as_geom;
   size_t as_smem = 0;
-  const bool paired = (MODE == MODE_FWD) && !force_single_warp() && (NT <= 5) &&
-                      as_geometry<TT, NA, NSA, ND, TTB_AS, NSB_AS>(a.in_ld, a.var_ld, (int)sizeof(Tin), NT, as_geom, as_smem);
-  const bool staged = (MODE == MODE_FWD) && !force_direct_loads() && (a.win.nw == NW) &&
-                      tma_geometry<TT, NS, TTB>(a.in_ld, a.var_ld, (int)sizeof(Tin), NT, geom, smem_bytes);
+  constexpr int ES = (int)sizeof(Tin);
+  constexpr bool GRAD = (MODE == MODE_GRAD);
+  // the gradient takes the staged path when grad_out is float32 (what autograd hands over)
+  const bool paired = (MODE == MODE_FWD || (GRAD && !a.go_f64)) && !force_single_warp() && (NT <= 5) &&
+                      as_geometry<TT, NA, NSA, ND, TTB_AS, NSB_AS>(GRAD ? a.go_ld * 4 : a.in_ld * ES, a.var_ld * ES, GRAD, L,
+                                                                   NT, as_geom, as_smem);
+  const bool staged = !force_direct_loads() && (a.win.nw == NW) &&
+                      ((MODE == MODE_FWD && tma_geometry<TT, NS, TTB>(a.in_ld, a.var_ld, ES, NT, geom, smem_bytes)) ||
+                       (GRAD && paired));
   for (int u0 = 0; u0 < a.n_utt; u0 += utt_per_launch) {
     const int nu = (a.n_utt - u0 < utt_per_launch) ? a.n_utt - u0 : utt_per_launch;
     p.urank0 = u0;
@@ -373,10 +378,11 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
       const bool stdw = CAN_STD && is_std_windows(a.win);
       const bool varg = (a.var_ld == 0);
       const int grid = nu * p.n_groups;
+      constexpr int AS_MODE = GRAD ? MODE_GRAD : MODE_FWD;  // MODE_SOLVE never gets here
       if (paired) {
 #define NNK_LAUNCH_AS(STDV, VARGV)                                                                                   \
   do {                                                                                                              \
-    auto kern = mlpg_fwd_as_kernel<Tin, NW, L, U, STDV, VARGV, TT, NA, NSA, ND, TTB_AS, NSB_AS>;                           \
+    auto kern = mlpg_fwd_as_kernel<Tin, NW, L, U, STDV, VARGV, AS_MODE, TT, NA, NSA, ND, TTB_AS, NSB_AS>;                  \
     NNK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)as_smem));         \
     kern<<<grid, 32 * (NA + 1), as_smem, st>>>(p, as_geom);                                                         \
   } while (0)

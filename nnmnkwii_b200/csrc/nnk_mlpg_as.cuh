@@ -24,16 +24,25 @@ namespace nnk {
 
 struct AsGeom {
   uint32_t sb_in;     // bytes of one input stage (one array)
-  uint32_t sb_ws;     // bytes of one scratch stage (backward sweep)
+  uint32_t sb_ws;     // bytes of the factor part of one backward stage
+  uint32_t sb_bw;     // bytes of one backward stage (factor tile [+ variance rows in GRAD mode])
   uint32_t ring_a;    // bytes of one assembler's input ring
   uint32_t off_pb;    // byte offset of the PB ring inside dynamic shared memory
 };
+
+// MODE_GRAD (paramgen/_mlpg.py:242-281, one banded solve + one stencil per chain instead of the
+// reference's dense T x T right-hand side): the right-hand side of chain c is column c of grad_out
+// (float32, staged in the slot the means occupy in MODE_FWD), and the backward sweep turns every
+// solution value x[t] into the nw gradient columns of row r = t + L,
+//     out[r][in_col + w * win_stride] = tau_w[r] * sum_i c[w][i] x[r - L + i],
+// re-staging the variance rows next to the factor tiles (the assemblers have retired by then and
+// their rings and the PB ring are free).
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <typename Tin, int NW, int L, int U, bool STD, bool VARG, int TT, int NA, int NSA, int ND, int TTB, int NSB>
+template <typename Tin, int NW, int L, int U, bool STD, bool VARG, int MODE, int TT, int NA, int NSA, int ND, int TTB, int NSB>
 __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid_constant__ MlpgParams<Tin, NW, L, U> p,
                                                                     const AsGeom g) {
   constexpr int S = L + U;
@@ -41,6 +50,8 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   constexpr int NR = S + 2;        // doubles per published band row: acc[0..S], b
   constexpr int NF = TT + NT - 1;  // frames an assembler converts per tile (TT + halo)
   constexpr int ES = (int)sizeof(Tin);
+  constexpr bool GRAD = (MODE == MODE_GRAD);
+  static_assert(MODE == MODE_FWD || MODE == MODE_GRAD, "staged kernel: forward or gradient");
   extern __shared__ __align__(128) unsigned char smem[];
   // barriers: input full [NA][NSA] | PB full [ND] | PB empty [ND] | scratch full [NSB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -81,19 +92,31 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
 
   const int npb = (T + L + TT - 1) / TT;  // band-row tiles: tile k holds rows r = k*TT - L + j, j < TT
   Tin* const outp = reinterpret_cast<Tin*>(p.out) + row0 * p.out_ld + ch.out_col;
+  float* const outg = reinterpret_cast<float*>(p.out) + row0 * p.out_ld + ch.in_col;  // GRAD: (T, D) float32
+
+  // column span [cmin, cmax] of the variance (and means) rows this group touches
+  const int lo_c = active ? ch.in_col : INT_MAX;
+  const int hi_c = active ? ch.in_col + (solve ? (NW - 1) * ch.win_stride : 0) : -1;
+  const int cmin = __reduce_min_sync(0xffffffffu, lo_c);
+  const int cmax = __reduce_max_sync(0xffffffffu, hi_c);
+  const int my_col = active ? ch.in_col : cmin;
+  const int my_stride = solve ? ch.win_stride : 0;
+  const int ldb_v = (int)(p.var_ld * ES);
+  const uint64_t g_v = (uint64_t)p.vars + (uint64_t)((VARG ? 0 : row0 * p.var_ld + cmin) * ES);
+  const uint32_t span_b = (uint32_t)(cmax - cmin + 1) * ES;
+  int colb[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) colb[w] = (my_col - cmin + w * my_stride) * ES;
 
   if (role < NA) {
     // =============================== assembler warp `role` ===========================================
-    const int lo_c = active ? ch.in_col : INT_MAX;
-    const int hi_c = active ? ch.in_col + (solve ? (NW - 1) * ch.win_stride : 0) : -1;
-    const int cmin = __reduce_min_sync(0xffffffffu, lo_c);
-    const int cmax = __reduce_max_sync(0xffffffffu, hi_c);
-    const int my_col = active ? ch.in_col : cmin;
-    const int my_stride = solve ? ch.win_stride : 0;
-    const int ldb_m = (int)(p.in_ld * ES), ldb_v = (int)(p.var_ld * ES);
-    const uint64_t g_m = (uint64_t)p.means + (uint64_t)((row0 * p.in_ld + cmin) * ES);
-    const uint64_t g_v = (uint64_t)p.vars + (uint64_t)((VARG ? 0 : row0 * p.var_ld + cmin) * ES);
-    const uint32_t span_b = (uint32_t)(cmax - cmin + 1) * ES;
+    // first staged array: the means rows (FWD) or the 32 grad_out columns of this group (GRAD, float32)
+    const int nlane = min(32, p.n_chain - grp * 32);
+    const int ldb_m = GRAD ? (int)(p.go_ld * 4) : (int)(p.in_ld * ES);
+    const uint64_t g_m = GRAD ? (uint64_t)p.go + (uint64_t)((row0 * p.go_ld + grp * 32) * 4)
+                              : (uint64_t)p.means + (uint64_t)((row0 * p.in_ld + cmin) * ES);
+    const uint32_t span_m = GRAD ? (uint32_t)nlane * 4u : span_b;
+    const int colg = (active ? lane : 0) * 4;
     unsigned char* ring = rings + (size_t)role * g.ring_a;
     uint64_t* my_full = in_full + role * NSA;
 
@@ -102,7 +125,7 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
       const int f_lo = max(0, k * TT - (NT - 1)), f_hi = min(T, k * TT + TT);
       const uint64_t A0 = g_m + (uint64_t)((int64_t)f_lo * ldb_m);
       const uint64_t a0 = A0 & ~(uint64_t)15;
-      const uint32_t nb = (uint32_t)(((A0 + (uint64_t)((f_hi - f_lo - 1) * (int64_t)ldb_m) + span_b + 15) & ~(uint64_t)15) - a0);
+      const uint32_t nb = (uint32_t)(((A0 + (uint64_t)((f_hi - f_lo - 1) * (int64_t)ldb_m) + span_m + 15) & ~(uint64_t)15) - a0);
       uint32_t nb2 = 0;
       uint64_t b0 = 0;
       if (!VARG) {
@@ -122,9 +145,6 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
 #pragma unroll
     for (int w = 0; w < NW; ++w)
       gtau[w] = VARG ? recip_in_dtype<Tin>::f(p.vars[my_col + w * my_stride]) : 0.0;
-    int colb[NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) colb[w] = (my_col - cmin + w * my_stride) * ES;
 
     // convert the NF frames of tile k (slot j <-> frame k*TT - (NT-1) + j; staged row = frame - f_lo),
     // assemble its TT band rows and publish them to PB slot `dst`
@@ -133,6 +153,7 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
       const int fbase = k * TT - (NT - 1);
       const int f_lo = max(0, fbase);
       double ft[NF][NW], fm[NF][NW];
+      float fg[NF];  // GRAD: grad_out of this lane's chain
 #pragma unroll
       for (int j = 0; j < NF; ++j) {
         const int f = fbase + j;
@@ -140,9 +161,18 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
         const bool edge = !FULL && ((m_edge == 0) || (f < m_edge) || (f >= T - m_edge));
         const int row = real ? (FULL ? j : f - f_lo) : 0;
         Tin mraw[NW];
+        if (GRAD) {
+          fg[j] = *reinterpret_cast<const float*>(sm_m + row * ldb_m + colg);
 #pragma unroll
-        for (int w = 0; w < NW; ++w) mraw[w] = *reinterpret_cast<const Tin*>(sm_m + row * ldb_m + colb[w]);
-        if (j >= NT - 1 && copy_lane && real) st_stream(outp + (int64_t)f * p.out_ld, mraw[0]);  // pass-through column
+          for (int w = 0; w < NW; ++w) mraw[w] = Tin(0);
+          // gradient of a pass-through column is grad_out itself
+          if (j >= NT - 1 && copy_lane && real) st_stream(outg + (int64_t)f * p.out_ld, fg[j]);
+        } else {
+          fg[j] = 0.f;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) mraw[w] = *reinterpret_cast<const Tin*>(sm_m + row * ldb_m + colb[w]);
+          if (j >= NT - 1 && copy_lane && real) st_stream(outp + (int64_t)f * p.out_ld, mraw[0]);  // pass-through column
+        }
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
           double tw;
@@ -164,6 +194,7 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
           acc[1] = -2.0 * (b[2] + c[2]);
           acc[2] = fma(-0.25, c[1], c[2]);
           bb = fm[j + 1][0] + fma(0.5, fm[j][1] - fm[j + 2][1], fma(-2.0, fm[j + 1][2], fm[j][2] + fm[j + 2][2]));
+          if (GRAD) bb = (double)fg[j + 1];
         } else {
 #pragma unroll
           for (int m = 0; m <= S; ++m) {
@@ -179,6 +210,7 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
           for (int w = 0; w < NW; ++w)
 #pragma unroll
             for (int i = 0; i < NT; ++i) bb = fma(p.win.c[w][i], fm[NT - 1 + j - i][w], bb);
+          if (GRAD) bb = (double)fg[j + U];  // band row j is frame fbase + U + j
         }
         double* row = dst + (size_t)j * (NR * 32) + lane;
 #pragma unroll
@@ -287,13 +319,24 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   __threadfence();
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncwarp();
-  unsigned char* ring = rings;  // every assembler has retired: reuse ring 0
+  unsigned char* ring = rings;  // every assembler has retired: reuse the input rings (and the PB ring behind them)
   const int nbt = (T + TTB - 1) / TTB;
+  // backward stage kb holds frames [t0, t0 + TTB) of the factor scratch; GRAD adds the variance rows
+  // [t0, min(T, t0 + TTB + L)) behind it (row r = t + L is emitted when x[t] becomes known)
   auto issue_ws = [&](int kb, int s) {
     const int t0 = (nbt - 1 - kb) * TTB;
     const uint32_t nb = (uint32_t)(min(T, t0 + TTB) - t0) * NT * 32 * 8;
-    mbar_expect_tx(ws_full + s, nb);
-    bulk_g2s(ring + (size_t)s * g.sb_ws, ws0 + (size_t)t0 * (NT * 32), nb, ws_full + s);
+    uint32_t nb2 = 0;
+    uint64_t b0 = 0;
+    if (GRAD && !VARG) {
+      const int r_hi = min(T, t0 + TTB + L);
+      const uint64_t B0 = g_v + (uint64_t)((int64_t)t0 * ldb_v);
+      b0 = B0 & ~(uint64_t)15;
+      nb2 = (uint32_t)(((B0 + (uint64_t)((r_hi - t0 - 1) * (int64_t)ldb_v) + span_b + 15) & ~(uint64_t)15) - b0);
+    }
+    mbar_expect_tx(ws_full + s, nb + nb2);
+    bulk_g2s(ring + (size_t)s * g.sb_bw, ws0 + (size_t)t0 * (NT * 32), nb, ws_full + s);
+    if (GRAD && !VARG) bulk_g2s(ring + (size_t)s * g.sb_bw + g.sb_ws, reinterpret_cast<const void*>(b0), nb2, ws_full + s);
   };
   if (lane == 0)
     for (int kb = 0; kb < NSB && kb < nbt; ++kb) issue_ws(kb, kb);
@@ -303,7 +346,35 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   // output pointer walks backwards with the sweep; lanes that do not own a chain store nothing
   const int64_t ostep = p.out_ld;
   Tin* op = outp + (int64_t)(T - 1) * ostep;
-  auto back = [&](const double* fr) {
+  float* og = outg + (int64_t)(T - 1 + L) * ostep;  // GRAD: row t + L
+  double gtau[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w)
+    gtau[w] = (GRAD && VARG) ? recip_in_dtype<Tin>::f(p.vars[my_col + w * my_stride]) : 0.0;
+
+  // GRAD: the nw gradient columns of row r from x[r - L .. r + U] = yw[0 .. S]; vrow = staged variance row r
+  auto emit = [&](int r, const unsigned char* vrow) {
+    const bool in = (r < T);
+    const bool edge = (m_edge == 0) || (r < m_edge) || (r >= T - m_edge);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      double sw;
+      if (STD) {
+        sw = (w == 0) ? yw[1] : (w == 1) ? 0.5 * (yw[2] - yw[0]) : fma(-2.0, yw[1], yw[0] + yw[2]);
+      } else {
+        sw = 0.0;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) sw = fma(p.win.c[w][i], yw[i], sw);
+      }
+      double tw;
+      if (VARG) tw = gtau[w];
+      else tw = recip_fast<Tin>::f(*reinterpret_cast<const Tin*>(vrow + colb[w]));
+      tw = (w > 0 && edge) ? 0.0 : tw;
+      st_stream_if(og + w * my_stride, (float)(tw * sw), solve && in && (w < p.win.nw));
+    }
+    og -= ostep;
+  };
+  auto back = [&](const double* fr, const unsigned char* vrow, int r) {
 #pragma unroll
     for (int j = S; j > 0; --j) yw[j] = yw[j - 1];
     // oldest terms first: only the last FMA (with y[t+1]) sits on the loop-carried chain
@@ -311,8 +382,12 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
 #pragma unroll
     for (int j = S; j >= 1; --j) y = fma(-fr[j * 32], yw[j], y);
     yw[0] = y;
-    st_stream_if(op, (Tin)y, solve);
-    op -= ostep;
+    if (GRAD) {
+      emit(r, vrow);
+    } else {
+      st_stream_if(op, (Tin)y, solve);
+      op -= ostep;
+    }
   };
   {
     int s = 0;
@@ -320,12 +395,27 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
     for (int kb = 0; kb < nbt; ++kb) {
       mbar_wait(ws_full + s, par);
       const int t0 = (nbt - 1 - kb) * TTB;
-      const double* smw = reinterpret_cast<const double*>(ring + (size_t)s * g.sb_ws) + lane;
-      if (t0 + TTB <= T) {
+      const double* smw = reinterpret_cast<const double*>(ring + (size_t)s * g.sb_bw) + lane;
+      // staged variance row of frame r sits at (r - t0) * ldb_v behind the factor tile
+      const unsigned char* smv = ring + (size_t)s * g.sb_bw + g.sb_ws +
+                                 (uint32_t)((g_v + (uint64_t)((int64_t)t0 * ldb_v)) & 15);
+      if (t0 + TTB + (GRAD ? L : 0) <= T) {
 #pragma unroll
-        for (int j = TTB - 1; j >= 0; --j) back(smw + j * (NT * 32));
+        for (int j = TTB - 1; j >= 0; --j) back(smw + j * (NT * 32), smv + (j + L) * ldb_v, t0 + j + L);
       } else {
-        for (int t = T - 1; t >= t0; --t) back(smw + (t - t0) * (NT * 32));
+        for (int t = T - 1; t >= t0; --t) {
+          const int r = t + L;
+          back(smw + (t - t0) * (NT * 32), smv + (r < T ? r - t0 : 0) * ldb_v, r);
+        }
+      }
+      if (GRAD && kb == nbt - 1) {
+        // drain: rows L-1 .. 0 see x[-1], x[-2], ... = 0 (this is the stage of t0 == 0: row r sits at r)
+        for (int r = L - 1; r >= 0; --r) {
+#pragma unroll
+          for (int j = S; j > 0; --j) yw[j] = yw[j - 1];
+          yw[0] = 0.0;
+          emit(r, smv + r * ldb_v);
+        }
       }
       __syncwarp();
       if (lane == 0 && kb + NSB < nbt) issue_ws(kb + NSB, s);
@@ -334,19 +424,26 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   }
 }
 
+// row_bytes_m / row_bytes_v: bytes of one staged row of the first array (means, or grad_out in GRAD
+// mode) and of the variances; half_l = L (GRAD stages TTB + L variance rows per backward tile)
 template <int TT, int NA, int NSA, int ND, int TTB, int NSB>
-static inline bool as_geometry(int64_t in_ld, int64_t var_ld, int es, int nt, AsGeom& g, size_t& smem_bytes) {
-  const int64_t ld = in_ld > var_ld ? in_ld : var_ld;
-  const size_t sb_in = ((size_t)(TT + nt - 1) * (size_t)ld * es + 32 + 15) / 16 * 16;
+static inline bool as_geometry(int64_t row_bytes_m, int64_t row_bytes_v, bool grad, int half_l, int nt, AsGeom& g,
+                               size_t& smem_bytes) {
+  const int64_t ld = row_bytes_m > row_bytes_v ? row_bytes_m : row_bytes_v;
+  const size_t sb_in = ((size_t)(TT + nt - 1) * (size_t)ld + 32 + 15) / 16 * 16;
   const size_t sb_ws = (size_t)TTB * nt * 32 * 8;
+  const size_t sb_var = grad ? ((size_t)(TTB + half_l) * (size_t)row_bytes_v + 32 + 15) / 16 * 16 : 0;
+  const size_t sb_bw = sb_ws + sb_var;
   size_t ring_a = ((size_t)NSA * 2 * sb_in + 127) / 128 * 128;
-  const size_t bwd = (size_t)NSB * sb_ws;
-  if ((size_t)NA * ring_a < bwd) ring_a = (bwd / NA + 127) / 128 * 128;
   const size_t pbb = (size_t)ND * TT * (nt + 1) * 32 * 8;
+  // the backward stages overlay the input rings and, behind them, the PB ring (both idle by then)
+  const size_t bwd = (size_t)NSB * sb_bw;
+  if ((size_t)NA * ring_a + pbb < bwd) ring_a = ((bwd - pbb) / NA + 127) / 128 * 128;
   const size_t tot = 512 + (size_t)NA * ring_a + pbb;
   if (tot > (size_t)100 * 1024) return false;
   g.sb_in = (uint32_t)sb_in;
   g.sb_ws = (uint32_t)sb_ws;
+  g.sb_bw = (uint32_t)sb_bw;
   g.ring_a = (uint32_t)ring_a;
   g.off_pb = (uint32_t)(512 + (size_t)NA * ring_a);
   smem_bytes = tot;

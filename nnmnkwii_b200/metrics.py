@@ -16,6 +16,7 @@ import math
 import numpy as np
 
 _logdb_const = 10.0 / np.log(10.0) * np.sqrt(2.0)  # metrics/__init__.py:5
+_ws_cache = {}
 
 
 def _dev(x, device=None):
@@ -63,10 +64,13 @@ def _reduce(call, device, B):
     from . import _device as dev
     from ._lib import check, lib
     need = int(lib.nnk_metric_workspace_bytes(max(1, B)))
-    ws = torch.empty(need, dtype=torch.uint8, device=device)
+    ws = _ws_cache.get(device)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)  # zeroed once; every call leaves it reusable
+        _ws_cache[device] = ws
     res = torch.zeros(2, dtype=torch.float64, device=device)  # [sum, count (int64 bits)]
     rc = call(ctypes.c_void_p(res.data_ptr()), ctypes.c_void_p(res.data_ptr() + 8),
-              ctypes.c_void_p(ws.data_ptr()), ctypes.c_int64(need), dev.current_stream_ptr(device))
+              ctypes.c_void_p(ws.data_ptr()), ctypes.c_int64(ws.numel()), dev.current_stream_ptr(device))
     check(rc, "nnk metric")
     s = float(res[0].item())
     c = int(res[1:2].view(torch.int64).item())

@@ -125,6 +125,45 @@ def test_mlpg_grad_vs_oracle():
                 g = G.mlpg_grad(m, v, ws, go)
                 assert g.dtype == np.float32 and g.shape == (T, sd * nw)
                 assert rel_err(g, oracle.mlpg_grad(m, v, ws, go)) < 2e-6
+    # more lengths around the tile sizes, global (D,) variances, float64 grad_output (direct-load kernel)
+    ws = windows_set()[2]
+    for T in (2, 4, 5, 8, 9, 16, 17, 31, 64, 65):
+        sd = 40
+        m = rng.random((T, sd * 3)).astype(np.float32)
+        v = (rng.random((T, sd * 3)) + 0.05).astype(np.float32)
+        v1 = (rng.random(sd * 3) + 0.05).astype(np.float32)
+        go = rng.standard_normal((T, sd)).astype(np.float32)
+        assert rel_err(G.mlpg_grad(m, v, ws, go), oracle.mlpg_grad(m, v, ws, go)) < 2e-6, T
+        assert rel_err(G.mlpg_grad(m, v1, ws, go), oracle.mlpg_grad(m, v1, ws, go)) < 2e-6, T
+        g64 = G.mlpg_grad(m, v, ws, go.astype(np.float64))
+        assert rel_err(g64, oracle.mlpg_grad(m, v, ws, go)) < 2e-6, T
+
+
+def test_mlpg_grad_batched_device_call():
+    """nnk_mlpg_grad on a ragged batch in one launch (what a batched autograd.MLPG would issue):
+    every utterance equals the single-utterance oracle result; rows of other utterances untouched."""
+    import torch
+    from nnmnkwii_b200 import _device as dev
+    from nnmnkwii_b200 import _lib
+    ws = windows_set()[2]
+    rng = np.random.default_rng(8)
+    sd = 59
+    lens = np.array([7, 300, 1, 64, 129, 33])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n = int(off[-1])
+    v = (rng.random((n, 3 * sd)) + 0.05).astype(np.float32)
+    go = rng.standard_normal((n, sd)).astype(np.float32)
+    dv, dgo = torch.from_numpy(v).cuda(), torch.from_numpy(go).cuda()
+    out = torch.zeros(n, 3 * sd, device="cuda")
+    dev.run_mlpg("grad", means=None, variances=dv, rhs=dgo, out=out, offsets=torch.from_numpy(off).cuda(), lengths=None,
+                 order=None, chains=dev.chains_on_device(dev.simple_chains(sd), dv.device), n_chain=sd,
+                 max_T=int(lens.max()), windows_c=_lib.make_windows(ws), in_ld=3 * sd, var_ld=3 * sd, go_ld=sd,
+                 out_ld=3 * sd, dtype_code=_lib.NNK_F32, go_f64=0, n_utt=len(lens), device=dv.device, check=True)
+    got = out.cpu().numpy()
+    for u in range(len(lens)):
+        a, b = off[u], off[u + 1]
+        want = oracle.mlpg_grad(np.zeros((b - a, 3 * sd), np.float32), v[a:b], ws, go[a:b])
+        assert rel_err(got[a:b], want) < 2e-6, u
 
 
 def test_unit_variance_mlpg_matrix(golden):
