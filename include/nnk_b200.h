@@ -216,9 +216,9 @@ int nnk_delta_features(const void* x, int32_t dtype, int32_t D, int64_t x_ld, co
  *   nnk_f0_metric    kind 0: sum of (x - y)^2 over frames with src_vuv + tgt_vuv >= 2; count = voiced
  *                    kind 1: the same on exp(x), exp(y)        (lf0_mean_squared_error, :141-165)
  *                    kind 2: sum of (src_vuv != tgt_vuv)       (vuv_error,           :181-190)
- * Deterministic (fixed-order fold of per-block partials).  workspace >= nnk_metric_workspace_bytes(B),
+ * Deterministic (fixed-order fold of per-block partials).  workspace >= nnk_metric_workspace_bytes(B, T),
  * zero-filled before its first use (each call leaves it reusable); one workspace per stream.         */
-int64_t nnk_metric_workspace_bytes(int32_t B);
+int64_t nnk_metric_workspace_bytes(int32_t B, int32_t T);
 int nnk_frame_metric(const void* X, const void* Y, int32_t dtype, int32_t B, int32_t T, int32_t D,
                      int64_t item_stride, int64_t frame_stride, const int32_t* lengths, int32_t kind, double* sum_out,
                      int64_t* count_out, void* workspace, int64_t workspace_bytes, void* stream);

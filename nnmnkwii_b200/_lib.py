@@ -148,7 +148,7 @@ def _load():
     L.nnk_delta_features.restype = ctypes.c_int
     L.nnk_delta_features.argtypes = [vp, i32, i32, i64, vp, vp, i32, i32, ctypes.POINTER(NnkWindows), vp, i64, vp]
     L.nnk_metric_workspace_bytes.restype = i64
-    L.nnk_metric_workspace_bytes.argtypes = [i32]
+    L.nnk_metric_workspace_bytes.argtypes = [i32, i32]
     L.nnk_frame_metric.restype = ctypes.c_int
     L.nnk_frame_metric.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, i64, vp]
     L.nnk_f0_metric.restype = ctypes.c_int

@@ -20,6 +20,8 @@
 namespace nnk {
 
 constexpr int MT_BLOCK = 256;
+constexpr int64_t MT_MAX_BLOCKS = 1 << 20;
+constexpr int MT_MIN_TILE_FRAMES = 46;  // narrow-frame tiles hold >= 46 frames (D < 128, float64)
 constexpr int MT_UNROLL = 4;
 
 struct MetricParams {
@@ -32,6 +34,7 @@ struct MetricParams {
   int64_t frame_stride; // elements between frames
   int B, T, D;
   int chunks;           // blocks per batch item
+  int64_t max_blk;      // partial slots in the workspace
   int kind;
   double* partial_sum;
   long long* partial_cnt;
@@ -49,7 +52,7 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   __syncthreads();
   double r = 0.0;
   if (threadIdx.x < 32) {
-    r = threadIdx.x < (MT_BLOCK / 32) ? sh[threadIdx.x] : 0.0;
+    r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
 #pragma unroll
     for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   }
@@ -73,7 +76,7 @@ __device__ __forceinline__ void finish(const MetricParams& p, double acc, long l
   if (!last) return;
   __threadfence();
   double ts = 0.0, tc = 0.0;
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += MT_BLOCK) {
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
     ts += __ldcg(p.partial_sum + i);
     tc += (double)__ldcg(p.partial_cnt + i);
   }
@@ -144,6 +147,106 @@ __global__ void __launch_bounds__(MT_BLOCK) frame_metric_kernel(const __grid_con
   finish(p, acc, cnt);
 }
 
+// Narrow frames (D < 128, frames contiguous): the warp-per-frame mapping above spends ~50 warp
+// instructions per frame on shuffles and the square root.  Here a block streams a TILE of F whole
+// frames (F * D contiguous elements of X and of Y, coalesced, 8 + 8 loads in flight per thread) into
+// shared memory as squared differences, then thread f adds up frame f (float64) and takes its square
+// root: ~7 warp instructions per frame.
+constexpr int MT_TILE_ELEMS = 11776;  // float32 elements of one tile (46 KB: static + dynamic stay under 48 KB)
+constexpr int MT_TBLOCK = 128;        // threads (= frames per tile): small blocks, many per SM
+
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { typedef float4 type; static constexpr int N = 4; };
+template <> struct Vec16<double> { typedef double2 type; static constexpr int N = 2; };
+
+__device__ __forceinline__ float4 sqdiff(float4 a, float4 b) {
+  float4 z = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+  return make_float4(z.x * z.x, z.y * z.y, z.z * z.z, z.w * z.w);
+}
+__device__ __forceinline__ double2 sqdiff(double2 a, double2 b) {
+  double2 z = make_double2(a.x - b.x, a.y - b.y);
+  return make_double2(z.x * z.x, z.y * z.y);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MT_TBLOCK) frame_metric_tile_kernel(const __grid_constant__ MetricParams p, const int F) {
+  typedef typename Vec16<T>::type V;
+  constexpr int VN = Vec16<T>::N;
+  extern __shared__ __align__(16) unsigned char tile_raw[];
+  T* sq0 = reinterpret_cast<T*>(tile_raw);
+  const int b = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x % p.chunks;
+  const int len = p.lengths ? min(max(p.lengths[b], 0), p.T) : p.T;
+  const T* X = reinterpret_cast<const T*>(p.x) + (int64_t)b * p.item_stride;
+  const T* Y = reinterpret_cast<const T*>(p.y) + (int64_t)b * p.item_stride;
+  const int D = p.D;
+  double acc = 0.0;
+  long long cnt = 0;
+  constexpr int UL = 8;   // scalar loads in flight per array and thread
+  constexpr int UV = 4;   // 16-byte loads in flight per array and thread
+  for (int f0 = chunk * F; f0 < len; f0 += p.chunks * F) {
+    const int nf = min(F, len - f0);
+    const int n = nf * D;
+    const T* xt = X + (int64_t)f0 * D;
+    const T* yt = Y + (int64_t)f0 * D;
+    // element e of the tile lives at sq[e] = sq0[mis + e]: shared memory mirrors the 16-byte phase of
+    // the global rows, so the aligned middle part moves as 16-byte vectors on both sides
+    const int mis = (int)((reinterpret_cast<uintptr_t>(xt) / sizeof(T)) % VN);
+    const bool vec_ok = (int)((reinterpret_cast<uintptr_t>(yt) / sizeof(T)) % VN) == mis;
+    T* sq = sq0 + mis;
+    const int head = vec_ok ? min(n, (VN - mis) % VN) : n;
+    const int nv = vec_ok ? (n - head) / VN : 0;
+    const int tail0 = head + nv * VN;
+    auto scalar_range = [&](int lo, int hi) {
+      for (int e0 = lo + threadIdx.x; e0 < hi; e0 += MT_TBLOCK * UL) {
+        T xv[UL], yv[UL];
+#pragma unroll
+        for (int u = 0; u < UL; ++u) {
+          const int e = e0 + u * MT_TBLOCK;
+          xv[u] = T(0); yv[u] = T(0);
+          if (e < hi) { xv[u] = ld_stream(xt + e); yv[u] = ld_stream(yt + e); }
+        }
+#pragma unroll
+        for (int u = 0; u < UL; ++u) {
+          const int e = e0 + u * MT_TBLOCK;
+          const T z = xv[u] - yv[u];  // difference and square in the input dtype, like z * z (:55-56)
+          if (e < hi) sq[e] = z * z;
+        }
+      }
+    };
+    scalar_range(0, head);
+    {
+      const V* xv4 = reinterpret_cast<const V*>(xt + head);
+      const V* yv4 = reinterpret_cast<const V*>(yt + head);
+      V* sv4 = reinterpret_cast<V*>(sq + head);
+      for (int i0 = threadIdx.x; i0 < nv; i0 += MT_TBLOCK * UV) {
+        V a[UV], c[UV];
+#pragma unroll
+        for (int u = 0; u < UV; ++u) {
+          const int i = i0 + u * MT_TBLOCK;
+          if (i < nv) { a[u] = __ldcs(xv4 + i); c[u] = __ldcs(yv4 + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < UV; ++u) {
+          const int i = i0 + u * MT_TBLOCK;
+          if (i < nv) sv4[i] = sqdiff(a[u], c[u]);
+        }
+      }
+    }
+    scalar_range(tail0, n);
+    __syncthreads();
+    for (int f = threadIdx.x; f < nf; f += MT_TBLOCK) {
+      const T* r = sq + f * D;
+      double s = 0.0;
+      for (int d = 0; d < D; ++d) s += (double)r[d];
+      acc += p.kind == 0 ? sqrt(s) : s;
+      cnt += 1;
+    }
+    __syncthreads();
+  }
+  finish(p, acc, cnt);
+}
+
 // kind 0: lf0 MSE (log domain), 1: lf0 MSE (linear domain: exp first), 2: vuv error
 template <typename T>
 __global__ void __launch_bounds__(MT_BLOCK) f0_metric_kernel(const __grid_constant__ MetricParams p) {
@@ -189,8 +292,8 @@ __global__ void __launch_bounds__(MT_BLOCK) f0_metric_kernel(const __grid_consta
   finish(p, acc, cnt);
 }
 
-static int pick_chunks(int B, int T, int frames_per_block_step) {
-  const int64_t want = 148 * 8;  // blocks in flight: 8 per SM
+static int pick_chunks(int B, int T, int frames_per_block_step, int per_sm = 8) {
+  const int64_t want = 148 * per_sm;  // blocks in flight per SM
   int64_t c = (want + B - 1) / B;
   const int64_t maxc = (T + frames_per_block_step - 1) / frames_per_block_step;
   if (c > maxc) c = maxc;
@@ -205,6 +308,17 @@ static void launch_frame(const MetricParams& p, cudaStream_t st) {
 
 template <typename T>
 static void dispatch_frame(MetricParams& p, cudaStream_t st) {
+  if (p.D < 128 && p.frame_stride == p.D) {
+    const int cap = MT_TILE_ELEMS * 4 / (int)sizeof(T) / p.D;  // frames per 48 KB tile
+    const int F = cap < MT_TBLOCK ? cap : MT_TBLOCK;
+    // a few tiles per block: many more blocks than SM slots, so the hardware block scheduler balances
+    // ragged lengths; the partial of block i always covers the same tiles (deterministic)
+    int64_t c = ((p.T + F - 1) / F + 3) / 4;  // ~4 tiles per block
+    if ((int64_t)p.B * c > p.max_blk) c = p.max_blk / p.B;
+    p.chunks = (int)(c < 1 ? 1 : c);
+    frame_metric_tile_kernel<T><<<(unsigned)(p.B * p.chunks), MT_TBLOCK, (size_t)F * p.D * sizeof(T) + 16, st>>>(p, F);
+    return;
+  }
   int G = 1;
   while (G < 32 && G < p.D) G <<= 1;
   p.chunks = pick_chunks(p.B, p.T, (MT_BLOCK / 32) * (32 / G) * MT_UNROLL);
@@ -218,12 +332,11 @@ static void dispatch_frame(MetricParams& p, cudaStream_t st) {
   }
 }
 
-constexpr int64_t MT_MAX_BLOCKS = 1 << 20;
-
 static int carve(void* workspace, int64_t workspace_bytes, int64_t blocks, MetricParams& p) {
   const int64_t need = 64 + blocks * 16;
   NNK_REQUIRE(workspace && workspace_bytes >= need, NNK_ERR_WORKSPACE, "metric workspace too small");
   char* w = reinterpret_cast<char*>(workspace);
+  p.max_blk = blocks;
   p.ticket = reinterpret_cast<unsigned int*>(w);
   p.partial_sum = reinterpret_cast<double*>(w + 64);
   p.partial_cnt = reinterpret_cast<long long*>(w + 64 + blocks * 8);
@@ -234,10 +347,15 @@ static int carve(void* workspace, int64_t workspace_bytes, int64_t blocks, Metri
 
 using namespace nnk;
 
-extern "C" int64_t nnk_metric_workspace_bytes(int32_t B) {
-  const int64_t blocks = (int64_t)(B > 0 ? B : 1) + 148 * 8;  // B * chunks <= B + 148*8
-  return 64 + blocks * 16;
+static int64_t max_blocks(int64_t B, int64_t T) {
+  if (B < 1) B = 1;
+  int64_t tiles = B * ((T + MT_MIN_TILE_FRAMES - 1) / MT_MIN_TILE_FRAMES);
+  if (tiles > MT_MAX_BLOCKS / 2) tiles = MT_MAX_BLOCKS / 2;
+  const int64_t spread = B + 148 * 16;  // the other kernels: B * chunks <= B + 148*16
+  return tiles > spread ? tiles : spread;
 }
+
+extern "C" int64_t nnk_metric_workspace_bytes(int32_t B, int32_t T) { return 64 + max_blocks(B, T) * 16; }
 
 extern "C" int nnk_frame_metric(const void* X, const void* Y, int32_t dtype, int32_t B, int32_t T, int32_t D,
                                 int64_t item_stride, int64_t frame_stride, const int32_t* lengths, int32_t kind,
@@ -254,11 +372,11 @@ extern "C" int nnk_frame_metric(const void* X, const void* Y, int32_t dtype, int
     return NNK_OK;
   }
   NNK_REQUIRE(X && Y, NNK_ERR_ARG, "NULL input");
-  NNK_REQUIRE((int64_t)B + 148 * 8 < MT_MAX_BLOCKS, NNK_ERR_ARG, "batch too large for one launch");
+  NNK_REQUIRE((int64_t)B + 148 * 16 < MT_MAX_BLOCKS / 2, NNK_ERR_ARG, "batch too large for one launch");
   MetricParams p{};
   p.x = X; p.y = Y; p.lengths = lengths; p.item_stride = item_stride; p.frame_stride = frame_stride;
   p.B = B; p.T = T; p.D = D; p.kind = kind; p.out_sum = sum_out; p.out_cnt = reinterpret_cast<long long*>(count_out);
-  const int rc = carve(workspace, workspace_bytes, (int64_t)B + 148 * 8, p);
+  const int rc = carve(workspace, workspace_bytes, max_blocks(B, T), p);
   if (rc) return rc;
   if (dtype == NNK_F32) dispatch_frame<float>(p, st);
   else dispatch_frame<double>(p, st);
@@ -282,13 +400,13 @@ extern "C" int nnk_f0_metric(const void* src_f0, const void* src_vuv, const void
     return NNK_OK;
   }
   NNK_REQUIRE(src_vuv && tgt_vuv && (kind == 2 || (src_f0 && tgt_f0)), NNK_ERR_ARG, "NULL input");
-  NNK_REQUIRE((int64_t)B + 148 * 8 < MT_MAX_BLOCKS, NNK_ERR_ARG, "batch too large for one launch");
+  NNK_REQUIRE((int64_t)B + 148 * 16 < MT_MAX_BLOCKS / 2, NNK_ERR_ARG, "batch too large for one launch");
   MetricParams p{};
   p.x = src_f0; p.y = tgt_f0; p.xv = src_vuv; p.yv = tgt_vuv; p.lengths = lengths;
   p.item_stride = item_stride; p.frame_stride = frame_stride;
   p.B = B; p.T = T; p.D = 1; p.kind = kind; p.out_sum = sum_out; p.out_cnt = reinterpret_cast<long long*>(count_out);
   p.chunks = pick_chunks(B, T, MT_BLOCK * MT_UNROLL);
-  const int rc = carve(workspace, workspace_bytes, (int64_t)B + 148 * 8, p);
+  const int rc = carve(workspace, workspace_bytes, max_blocks(B, T), p);
   if (rc) return rc;
   if (dtype == NNK_F32) f0_metric_kernel<float><<<(unsigned)(B * p.chunks), MT_BLOCK, 0, st>>>(p);
   else f0_metric_kernel<double><<<(unsigned)(B * p.chunks), MT_BLOCK, 0, st>>>(p);

@@ -57,13 +57,13 @@ def _lengths_on(device, lengths, B):
     return l.contiguous()  # the reference zips (X, Y, lengths): the shorter of the two bounds the loop
 
 
-def _reduce(call, device, B):
+def _reduce(call, device, B, T):
     """Run one of the C-ABI reductions; returns (sum, count) as Python numbers (synchronises)."""
     import torch
 
     from . import _device as dev
     from ._lib import check, lib
-    need = int(lib.nnk_metric_workspace_bytes(max(1, B)))
+    need = int(lib.nnk_metric_workspace_bytes(max(1, B), max(1, T)))
     ws = _ws_cache.get(device)
     if ws is None or ws.numel() < need:
         ws = torch.zeros(need, dtype=torch.uint8, device=device)  # zeroed once; every call leaves it reusable
@@ -89,7 +89,7 @@ def _frame_metric(X, Y, B, T, D, lengths, kind):
     def call(sum_p, cnt_p, ws_p, ws_n, stream):
         return lib.nnk_frame_metric(x.data_ptr(), y.data_ptr(), code, nb, T, D, T * D, D,
                                     l.data_ptr() if l is not None else None, kind, sum_p, cnt_p, ws_p, ws_n, stream)
-    return _reduce(call, device, nb)
+    return _reduce(call, device, nb, T)
 
 
 def _f0_metric(arrays, B, T, lengths, kind):
@@ -111,7 +111,7 @@ def _f0_metric(arrays, B, T, lengths, kind):
         return lib.nnk_f0_metric(xf.data_ptr() if xf is not None else None, xv.data_ptr(),
                                  yf.data_ptr() if yf is not None else None, yv.data_ptr(), code, nb, T, T, 1,
                                  l.data_ptr() if l is not None else None, kind, sum_p, cnt_p, ws_p, ws_n, stream)
-    return _reduce(call, device, nb)
+    return _reduce(call, device, nb, T)
 
 
 def _numel(shape):

@@ -68,3 +68,23 @@ def test_masked_melcd_large_batch_properties():
     Yw = torch.randn(7, 50, 513, device="cuda", generator=g)
     want = float(M._logdb_const * (Xw.double() - Yw.double()).pow(2).sum(-1).sqrt().mean())
     assert abs(M.melcd(Xw, Yw) - want) / want < 1e-9
+
+
+def test_masked_melcd_alignment_phases():
+    """Tiles start at every 16-byte phase (odd D, odd T) and X / Y may sit at different phases."""
+    import torch
+    from nnmnkwii_b200 import metrics as M
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for dt, tol in ((torch.float32, 1e-6), (torch.float64, 1e-12)):
+        for D in (1, 3, 25, 26, 59, 127):
+            B, T = 9, 301
+            X = torch.randn(B, T, D, device="cuda", generator=g, dtype=dt)
+            buf = torch.randn(B * T * D + 3, device="cuda", generator=g, dtype=dt)
+            lens = [301, 0, 5, 129, 128, 127, 300, 1, 77]
+            mask = (torch.arange(T)[None, :] < torch.tensor(lens)[:, None]).cuda()
+            for shift in (0, 1, 3):
+                Y = buf[shift:shift + B * T * D].view(B, T, D)
+                frame = (X.double() - Y.double()).pow(2).sum(-1).sqrt()
+                want = float(M._logdb_const * (frame * mask).sum() / sum(lens))
+                got = M.melcd(X, Y, lens)
+                assert abs(got - want) / want < tol, (dt, D, shift)
