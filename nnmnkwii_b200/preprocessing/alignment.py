@@ -191,7 +191,7 @@ class IterativeDTWAligner(object):
         from sklearn.mixture import GaussianMixture
 
         from . import trim_zeros_frames
-        from ._gmm_convert import FramewiseGMMConverter
+        from ..baseline.gmm import MLPG
 
         X, Y = XY
         assert X.ndim == 3 and Y.ndim == 3
@@ -228,10 +228,10 @@ class IterativeDTWAligner(object):
                                   random_state=self.random_state)
             XYj = np.concatenate((X_aligned, Y_aligned), axis=-1).reshape(-1, X.shape[-1] * 2)
             gmm.fit(XYj)
-            conv = FramewiseGMMConverter(gmm)
-            for idx in range(len(Xc)):
-                x = trim_zeros_frames(Xc[idx])
-                Xc[idx][: len(x)] = conv.transform(x)
+            paramgen = MLPG(gmm, windows=[(0, 0, np.array([1.0]))])  # no delta (alignment.py:179-180)
+            trimmed = [trim_zeros_frames(Xc[idx]) for idx in range(len(Xc))]
+            for idx, y in enumerate(paramgen.transform_batch(trimmed)):  # one device pass for all utterances
+                Xc[idx][: len(y)] = y
         # finally gather the ORIGINAL X along the last paths (alignment.py:186-188)
         if res is not None:
             out_rows = X_aligned.shape[1]

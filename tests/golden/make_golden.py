@@ -146,6 +146,26 @@ def main():
             M.vuv_error(va, vb), M.vuv_error(va, vb, lens), M.vuv_error(va[:, :, None], vb[:, :, None], lens),
             M.melcd(f0a, f0b, lens), M.mean_squared_error(f0a, f0b, lens),
         ], dtype=np.float64)
+    # GMM-based conversion: baseline.gmm.MLPG / MLPGBase on a fitted joint GMM
+    from sklearn.mixture import GaussianMixture
+    from nnmnkwii.baseline.gmm import MLPG as RefGMMMLPG
+    from nnmnkwii.baseline.gmm import MLPGBase as RefMLPGBase
+    gr = np.random.default_rng(99)
+    dim = 12  # = 2 windows x 6 static dims = 3 windows x 4 static dims
+    base = gr.standard_normal((400, dim))
+    joint = np.concatenate([base + 0.3 * gr.standard_normal((400, dim)),
+                            0.7 * base + 0.5 + 0.3 * gr.standard_normal((400, dim))], axis=-1)
+    gmm = GaussianMixture(n_components=4, covariance_type="full", random_state=0).fit(joint)
+    src = base[:50] + 0.1 * gr.standard_normal((50, dim))
+    out["gmm_means"], out["gmm_covars"], out["gmm_weights"], out["gmm_src"] = gmm.means_, gmm.covariances_, gmm.weights_, src
+    out["gmm_default"] = RefGMMMLPG(gmm).transform(src)
+    out["gmm_w3"] = RefGMMMLPG(gmm, windows=windows_set()[2]).transform(src)
+    out["gmm_w3_diff"] = RefGMMMLPG(gmm, windows=windows_set()[2], diff=True).transform(src)
+    out["gmm_w3_swap"] = RefGMMMLPG(gmm, windows=windows_set()[2], swap=True).transform(src)
+    out["gmm_static"] = RefGMMMLPG(gmm, windows=[(0, 0, np.array([1.0]))]).transform(src)
+    out["gmm_static_f32"] = RefGMMMLPG(gmm, windows=[(0, 0, np.array([1.0]))]).transform(src.astype(np.float32))
+    out["gmm_base_2d"] = RefMLPGBase(gmm, diff=True).transform(src)
+    out["gmm_base_1d"] = RefMLPGBase(gmm).transform(src[3])
     np.savez_compressed(os.path.join(HERE, "mlpg_reference_golden.npz"), **out)
 
     # DTW (restated oracle; see module docstring)
