@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnnk_b200.so")
+LIB_PATH = os.environ.get("NNK_LIB_PATH") or os.path.join(_HERE, "libnnk_b200.so")  # NNK_LIB_PATH: A/B builds
 
 NNK_OK, NNK_ERR_ARG, NNK_ERR_UNSUPPORTED, NNK_ERR_CUDA, NNK_ERR_WORKSPACE, NNK_ERR_NOT_PD = 0, -1, -2, -3, -4, -5
 NNK_F32, NNK_F64 = 0, 1

@@ -24,6 +24,12 @@
 #include "nnk_mlpg_tma.cuh"
 #include "nnk_mlpg_as.cuh"
 
+// assembler warps per chain group and TMA stages per assembler (A/B builds: -DNNK_AS_NA=2 -DNNK_AS_NSA=2)
+#ifndef NNK_AS_NA
+#define NNK_AS_NA 3
+#define NNK_AS_NSA 1
+#endif
+
 namespace nnk {
 
 __device__ __forceinline__ double load_go(const void* go, int is_f64, int64_t idx) {
@@ -357,12 +363,14 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   // forward solves go through the TMA-staged kernel unless the rows are too wide for its ring
   TmaGeom geom;
   size_t smem_bytes = 0;
-  constexpr int TT = 4, NS = 4, TTB = 4, NA = 2, NSA = 2, ND = 4;
-  constexpr int TTB_AS = 8, NSB_AS = 4;  // backward-sweep scratch ring of the paired kernel: 32 frames in flight
-  AsGeom as_geom;
-  size_t as_smem = 0;
   constexpr int ES = (int)sizeof(Tin);
   constexpr bool GRAD = (MODE == MODE_GRAD);
+  constexpr bool GRAD_MODE = GRAD;
+  constexpr int TT = 4, NS = 4, TTB = 4, NA = NNK_AS_NA, NSA = NNK_AS_NSA, ND = 4;
+  // backward-sweep scratch ring of the paired kernel: 64 frames in flight (32 when the variance rows ride along)
+  constexpr int TTB_AS = 8, NSB_AS = GRAD_MODE ? 4 : 8;
+  AsGeom as_geom;
+  size_t as_smem = 0;
   // the gradient takes the staged path when grad_out is float32 (what autograd hands over)
   const bool paired = (MODE == MODE_FWD || (GRAD && !a.go_f64)) && !force_single_warp() && (NT <= 5) &&
                       as_geometry<TT, NA, NSA, ND, TTB_AS, NSB_AS>(GRAD ? a.go_ld * 4 : a.in_ld * ES, a.var_ld * ES, GRAD, L,
@@ -448,6 +456,17 @@ extern "C" size_t nnk_mlpg_workspace_bytes(int32_t n_utt, int32_t n_chain, int32
   const size_t groups = (size_t)((n_chain + 31) / 32);
   return (size_t)n_utt * groups * (size_t)max_T * (size_t)(S + 1) * 32 * sizeof(double);
 }
+
+#ifdef NNK_AS_PROF
+// debug builds only: read and clear the phase counters of mlpg_fwd_as_kernel (synchronises)
+extern "C" int nnk_as_prof_read(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, nnk::g_as_prof, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(nnk::g_as_prof, z, sizeof(z));
+  return 0;
+}
+#endif
 
 extern "C" int nnk_mlpg_fwd(const nnk_mlpg_args_t* a, void* stream) {
   int r = check_args(a, false);

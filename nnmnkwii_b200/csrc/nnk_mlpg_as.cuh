@@ -38,6 +38,16 @@ struct AsGeom {
 // re-staging the variance rows next to the factor tiles (the assemblers have retired by then and
 // their rings and the PB ring are free).
 
+#ifdef NNK_AS_PROF
+// A/B instrumentation (build with NNK_NVCC_EXTRA=-DNNK_AS_PROF): cycles per role and phase, summed over CTAs
+__device__ unsigned long long g_as_prof[16];
+#define AS_TICK(var) const long long var = clock64()
+#define AS_ACC(slot, t0, t1) prof[slot] += (t1) - (t0)
+#else
+#define AS_TICK(var)
+#define AS_ACC(slot, t0, t1)
+#endif
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -120,8 +130,10 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
     unsigned char* ring = rings + (size_t)role * g.ring_a;
     uint64_t* my_full = in_full + role * NSA;
 
-    // tile k stages frames [f_lo, f_hi) = [max(0, k*TT - (NT-1)), min(T, k*TT + TT))  (never empty)
-    auto issue_in = [&](int k, int s) {  // lane 0 only
+    // tile k stages frames [f_lo, f_hi) = [max(0, k*TT - (NT-1)), min(T, k*TT + TT))  (never empty);
+    // PREF: only pull the two ranges into L2 (issued PFD turns of this warp ahead of the real copy)
+    auto issue_in = [&](auto pref_tag, int k, int s) {  // lane 0 only
+      constexpr bool PREF = decltype(pref_tag)::value;
       const int f_lo = max(0, k * TT - (NT - 1)), f_hi = min(T, k * TT + TT);
       const uint64_t A0 = g_m + (uint64_t)((int64_t)f_lo * ldb_m);
       const uint64_t a0 = A0 & ~(uint64_t)15;
@@ -133,13 +145,22 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
         b0 = B0 & ~(uint64_t)15;
         nb2 = (uint32_t)(((B0 + (uint64_t)((f_hi - f_lo - 1) * (int64_t)ldb_v) + span_b + 15) & ~(uint64_t)15) - b0);
       }
+      if (PREF) {
+        bulk_prefetch_l2(reinterpret_cast<const void*>(a0), nb);
+        if (!VARG) bulk_prefetch_l2(reinterpret_cast<const void*>(b0), nb2);
+        return;
+      }
       mbar_expect_tx(my_full + s, nb + nb2);
       bulk_g2s(ring + (size_t)s * 2 * g.sb_in, reinterpret_cast<const void*>(a0), nb, my_full + s);
       if (!VARG) bulk_g2s(ring + (size_t)s * 2 * g.sb_in + g.sb_in, reinterpret_cast<const void*>(b0), nb2, my_full + s);
     };
-    if (lane == 0)
+    constexpr int PFD = 2;  // L2 prefetch distance in turns of this warp beyond its staged tiles
+    if (lane == 0) {
       for (int i = 0; i < NSA; ++i)
-        if (role + i * NA < npb) issue_in(role + i * NA, i);
+        if (role + i * NA < npb) issue_in(FullTile<false>{}, role + i * NA, i);
+      for (int i = NSA; i < NSA + PFD; ++i)
+        if (role + i * NA < npb) issue_in(FullTile<true>{}, role + i * NA, 0);
+    }
 
     double gtau[NW];
 #pragma unroll
@@ -148,7 +169,7 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
 
     // convert the NF frames of tile k (slot j <-> frame k*TT - (NT-1) + j; staged row = frame - f_lo),
     // assemble its TT band rows and publish them to PB slot `dst`
-    auto do_tile = [&](auto full_tag, int k, const unsigned char* sm_m, const unsigned char* sm_v, double* dst) {
+    auto do_tile = [&](auto full_tag, int k, const unsigned char* sm_m, const unsigned char* sm_v, double* dst, int stage) {
       constexpr bool FULL = decltype(full_tag)::value;
       const int fbase = k * TT - (NT - 1);
       const int f_lo = max(0, fbase);
@@ -182,6 +203,12 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
           ft[j][w] = tw;
           fm[j][w] = tw * (double)mraw[w];
         }
+      }
+      // the staged rows now live in registers: refill this stage before assembling / publishing
+      __syncwarp();
+      if (lane == 0) {
+        if (k + NSA * NA < npb) issue_in(FullTile<false>{}, k + NSA * NA, stage);
+        if (k + (NSA + PFD) * NA < npb) issue_in(FullTile<true>{}, k + (NSA + PFD) * NA, 0);
       }
 #pragma unroll
       for (int j = 0; j < TT; ++j) {
@@ -221,23 +248,34 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
 
     int s = 0;
     uint32_t par = 0;
+#ifdef NNK_AS_PROF
+    long long prof[4] = {0, 0, 0, 0};
+#endif
     for (int k = role; k < npb; k += NA) {
       const int ps = k % ND;
+      AS_TICK(c0);
       mbar_wait_parked(pb_empty + ps, (uint32_t)(((k / ND) & 1) ^ 1));  // the solver has drained this PB slot
+      AS_TICK(c1);
       mbar_wait(my_full + s, par);
+      AS_TICK(c2);
+      AS_ACC(0, c0, c1);
+      AS_ACC(1, c1, c2);
       double* dst = pb + (size_t)ps * (TT * NR * 32);
       const int f_lo = max(0, k * TT - (NT - 1));
       const uint32_t mis_m = (uint32_t)((g_m + (uint64_t)((int64_t)f_lo * ldb_m)) & 15);
       const uint32_t mis_v = (uint32_t)((g_v + (uint64_t)((int64_t)f_lo * ldb_v)) & 15);
       const unsigned char* sm_m = ring + (size_t)s * 2 * g.sb_in + mis_m;
       const unsigned char* sm_v = ring + (size_t)s * 2 * g.sb_in + g.sb_in + mis_v;
-      if (m_edge > 0 && k * TT - (NT - 1) >= m_edge && k * TT + TT <= T - m_edge) do_tile(FullTile<true>{}, k, sm_m, sm_v, dst);
-      else do_tile(FullTile<false>{}, k, sm_m, sm_v, dst);
+      if (m_edge > 0 && k * TT - (NT - 1) >= m_edge && k * TT + TT <= T - m_edge) do_tile(FullTile<true>{}, k, sm_m, sm_v, dst, s);
+      else do_tile(FullTile<false>{}, k, sm_m, sm_v, dst, s);
       mbar_arrive(pb_full + ps);  // release: this lane's rows are visible to the solver
-      __syncwarp();
-      if (lane == 0 && k + NSA * NA < npb) issue_in(k + NSA * NA, s);
       if (++s == NSA) { s = 0; par ^= 1; }
+      AS_TICK(c3);
+      AS_ACC(2, c2, c3);
     }
+#ifdef NNK_AS_PROF
+    if (lane == 0) for (int i = 0; i < 3; ++i) atomicAdd(g_as_prof + i, (unsigned long long)prof[i]);
+#endif
     return;
   }
 
@@ -253,6 +291,9 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   }
   double iv1 = 0.0;
   int bad = 0;
+#ifdef NNK_AS_PROF
+  long long prof[4] = {0, 0, 0, 0};
+#endif
 
   auto eliminate = [&](int t, const double* row) {
     double acc[S + 1];
@@ -298,7 +339,10 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
     int ps = 0;
     uint32_t ppar = 0;
     for (int k = 0; k < npb; ++k) {
+      AS_TICK(c0);
       mbar_wait(pb_full + ps, ppar);
+      AS_TICK(c1);
+      AS_ACC(0, c0, c1);
       const double* src = pb + (size_t)ps * (TT * NR * 32) + lane;
       const int r0 = k * TT - L;  // row of the first band row in this tile
       if (r0 >= 0 && r0 + TT <= T) {
@@ -311,6 +355,8 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
       }
       mbar_arrive(pb_empty + ps);
       if (++ps == ND) { ps = 0; ppar ^= 1; }
+      AS_TICK(c2);
+      AS_ACC(1, c1, c2);
     }
   }
   if (bad && solve) report_not_pd(p.status, utt, chain, bad);
@@ -393,7 +439,10 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
     int s = 0;
     uint32_t par = 0;
     for (int kb = 0; kb < nbt; ++kb) {
+      AS_TICK(c0);
       mbar_wait(ws_full + s, par);
+      AS_TICK(c1);
+      AS_ACC(2, c0, c1);
       const int t0 = (nbt - 1 - kb) * TTB;
       const double* smw = reinterpret_cast<const double*>(ring + (size_t)s * g.sb_bw) + lane;
       // staged variance row of frame r sits at (r - t0) * ldb_v behind the factor tile
@@ -420,8 +469,13 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
       __syncwarp();
       if (lane == 0 && kb + NSB < nbt) issue_ws(kb + NSB, s);
       if (++s == NSB) { s = 0; par ^= 1; }
+      AS_TICK(c2);
+      AS_ACC(3, c1, c2);
     }
   }
+#ifdef NNK_AS_PROF
+  if (lane == 0) for (int i = 0; i < 4; ++i) atomicAdd(g_as_prof + 4 + i, (unsigned long long)prof[i]);
+#endif
 }
 
 // row_bytes_m / row_bytes_v: bytes of one staged row of the first array (means, or grad_out in GRAD

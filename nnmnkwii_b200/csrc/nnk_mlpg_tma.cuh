@@ -77,6 +77,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// L2 prefetch of a 16-byte aligned range (no shared memory, no completion tracking): the later bulk
+// copy of the same range then pays L2 instead of HBM latency
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 struct TmaGeom {
   uint32_t sb_in;  // bytes of one input stage (one array)
   uint32_t sb_ws;  // bytes of one scratch stage
