@@ -385,7 +385,7 @@ def run_ours(args):
                      "dram__bytes_read.sum 434.4 MB + dram__bytes_write.sum 266.4 MB per launch; the excess over the "
                      "algorithmic bytes is the float64 factor scratch round trip)", "peak_source": peak_src, "kernel": ("mlpg_kernel<float,3,1,1,FWD> (register prefetch)" if os.environ.get("NNK_MLPG_DIRECT") == "1" else
                                 "mlpg_fwd_tma_kernel<float,3,1,1,STD> (single warp)" if os.environ.get("NNK_MLPG_SINGLE") == "1" else
-                                "mlpg_fwd_as_kernel<float,3,1,1,STD> (2 assembler warps + 1 solver warp per 32 chains)"),
+                                "mlpg_fwd_as_kernel<float,3,1,1,STD> (3 assembler warps + 1 solver warp per 32 chains)"),
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * n_rows},
         "cpu_baseline": cpu_base,
         "clocks": clocks,

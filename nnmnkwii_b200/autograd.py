@@ -51,6 +51,30 @@ class MLPG(Function):
         return g.to(means.device), None, None
 
 
+class MLPGBatch(Function):
+    """Additive: :class:`MLPG` over a whole mini-batch -- ``(B, Tmax, D)`` zero-padded or flat
+    ``(sum_T, D)`` means with per-utterance ``lengths`` -- one forward and one backward kernel launch
+    for all utterances (the reference's ``MLPG`` is 2-D only and is looped over the batch).
+    Per-frame variances of the same shape, or global ``(D,)``.  Returns float32."""
+
+    @staticmethod
+    def forward(ctx, means, variances, windows, lengths):
+        assert means.dim() in (2, 3)
+        ctx.windows = windows
+        ctx.lengths = [int(n) for n in (lengths.tolist() if torch.is_tensor(lengths) else lengths)]
+        ctx.save_for_backward(means, variances)
+        device = _cuda_device(means)
+        y = G.mlpg_batch(means.detach().to(device), variances.detach().to(device), windows, lengths=ctx.lengths)
+        return y.to(torch.float32).to(means.device)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        means, variances = ctx.saved_tensors
+        device = _cuda_device(means)
+        g = G.mlpg_grad_batch(variances.detach().to(device), ctx.windows, grad_output.detach().to(device), ctx.lengths)
+        return g.to(means.device), None, None, None
+
+
 class UnitVarianceMLPG(Function):
     r"""MLPG for unit-variance inputs, ``y = R \mu`` (mlpg.py:70-172).
 
@@ -115,11 +139,16 @@ def mlpg(means, variances, windows):
     return MLPG.apply(means, variances, windows)
 
 
+def mlpg_batch(means, variances, windows, lengths):
+    """Additive: batched :func:`mlpg` (see :class:`MLPGBatch`)."""
+    return MLPGBatch.apply(means, variances, windows, lengths)
+
+
 def unit_variance_mlpg(R, means):
     """Special case of MLPG assuming unit variances (mlpg.py:202-217).  NB argument order
     ``(R, means)`` here, ``(means, R)`` for ``UnitVarianceMLPG.apply`` -- as in the reference."""
     return UnitVarianceMLPG.apply(means, R)
 
 
-__all__ = ["MLPG", "UnitVarianceMLPG", "mlpg", "unit_variance_mlpg"]
+__all__ = ["MLPG", "MLPGBatch", "UnitVarianceMLPG", "mlpg", "mlpg_batch", "unit_variance_mlpg"]
 _ = np  # numpy is part of the reference module's namespace

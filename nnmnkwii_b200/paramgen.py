@@ -26,6 +26,7 @@ from . import _lib
 from .bandmat import BandMat
 
 __all__ = [
+    "mlpg_grad_batch",
     "build_win_mats", "mlpg", "mlpg_grad", "full_window_mat", "unit_variance_mlpg_matrix", "reshape_means",
     "StreamLayout", "merlin_layout", "mlpg_batch",
 ]
@@ -339,6 +340,78 @@ def mlpg_grad(mean_frames, variance_frames, windows, grad_output):
     if is_t:
         return out
     return out.cpu().numpy()
+
+
+def mlpg_grad_batch(variances, windows, grad_output, lengths, layout=None):
+    """Batched :func:`mlpg_grad` on the device (additive API): the gradients of
+    ``mlpg_batch(means, variances, windows, lengths, layout=layout)`` with respect to ``means`` for
+    every utterance of the batch in ONE launch of ``nnk_mlpg_grad``.
+
+    Args:
+        variances: CUDA tensor, flat ``(sum_T, D)`` / padded ``(B, Tmax, D)`` per-frame variances,
+            or ``(D,)`` global.
+        grad_output: CUDA tensor ``(sum_T, D_out)`` / ``(B, Tmax, D_out)``, the gradient with respect
+            to the generated trajectories.
+        lengths: frames per utterance.
+
+    Returns:
+        float32 CUDA tensor shaped like the means (``(sum_T, D)`` or ``(B, Tmax, D)``); rows beyond
+        an utterance's length (padded form) are zero.
+    """
+    import torch
+
+    from . import _device as dev
+
+    dev.require_cuda()
+    assert _is_torch(grad_output) and grad_output.is_cuda, "device tensors only (no CPU fallback)"
+    device = grad_output.device
+    padded = grad_output.dim() == 3
+    lens_np = np.asarray(lengths.cpu() if _is_torch(lengths) else lengths, dtype=np.int64)
+    go = grad_output.detach()
+    if go.dtype not in (torch.float32, torch.float64):
+        go = go.to(torch.float32)
+    go = go.contiguous()
+    v = variances.detach().to(device)
+    if v.dtype not in (torch.float32, torch.float64):
+        v = v.to(torch.float64)
+    var1d = v.dim() == 1
+    D = v.shape[-1]
+    if layout is None:
+        layout = StreamLayout.single(D, len(windows))
+    assert layout.D_in == D and go.shape[-1] == layout.D_out
+    if padded:
+        B, Tmax = go.shape[0], go.shape[1]
+        off_np = np.arange(B + 1, dtype=np.int64) * Tmax
+        lens_t = torch.from_numpy(lens_np.astype(np.int32)).to(device)
+        n_rows = B * Tmax
+        if not var1d:
+            v = v.expand(B, Tmax, D)
+    else:
+        off_np = _offsets_from(lens_np, None, go.shape[0])
+        lens_t = None
+        n_rows = go.shape[0]
+        if not var1d:
+            v = v.expand(n_rows, D)
+    v = v.contiguous()  # materialises stride-0 expanded variances
+    max_T = int(lens_np.max(initial=0))
+    n_utt = len(lens_np)
+    out = torch.zeros((n_rows, D), dtype=torch.float32, device=device)
+    if n_utt and max_T and layout.n_chain:
+        # the gradient kernel indexes grad_output by chain: chain c reads column c, so route the
+        # layout's output columns to chain order (identity for a single stream)
+        out_cols = torch.from_numpy(layout.chains["out_col"].astype(np.int64)).to(device)
+        go2 = go.reshape(n_rows, layout.D_out)
+        if not np.array_equal(layout.chains["out_col"], np.arange(layout.n_chain)):
+            go2 = go2.index_select(1, out_cols).contiguous()
+        dev.run_mlpg(
+            "grad", means=None, variances=v, rhs=go2, out=out,
+            offsets=torch.from_numpy(off_np).to(device), lengths=lens_t,
+            order=torch.from_numpy(np.argsort(-lens_np, kind="stable").astype(np.int32)).to(device),
+            chains=dev.chains_on_device(layout.chains, device), n_chain=layout.n_chain, max_T=max_T,
+            windows_c=_lib.make_windows(windows), in_ld=D, var_ld=0 if var1d else D, go_ld=layout.n_chain, out_ld=D,
+            dtype_code=dev.torch_dtype_code(v.dtype), go_f64=int(go2.dtype == torch.float64), n_utt=n_utt,
+            device=device, check=True)
+    return out.reshape(go.shape[0], go.shape[1], D) if padded else out
 
 
 def unit_variance_mlpg_matrix(windows, T):

@@ -166,3 +166,40 @@ def test_cfg3_full_size_unit_variance():
     (gx,) = torch.autograd.grad(AF.unit_variance_mlpg(R, mu), mu, o)
     rhs = (mu.detach().double() * gx.double()).sum()
     assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5
+
+
+def test_batched_mlpg_autograd_matches_per_utterance():
+    """Additive MLPGBatch: one launch per direction for a ragged mini-batch == MLPG applied per utterance."""
+    import torch
+    from nnmnkwii_b200 import autograd as AF
+    ws = windows_set()[2]
+    g = torch.Generator().manual_seed(21)
+    sd, lens = 37, [50, 1, 33, 128, 7]
+    B, Tmax, D = len(lens), max(lens), 3 * sd
+    means = torch.randn(B, Tmax, D, generator=g)
+    var = torch.rand(B, Tmax, D, generator=g) + 0.1
+    w = torch.randn(B, Tmax, sd, generator=g)
+    mask = (torch.arange(Tmax)[None, :] < torch.tensor(lens)[:, None]).float()[:, :, None]
+    for device in ("cuda", "cpu"):
+        for gvar in (False, True):
+            v = (var[0, 0] if gvar else var).to(device)
+            m = (means * mask).to(device).requires_grad_(True)
+            y = AF.mlpg_batch(m, v, ws, lens)
+            assert y.shape == (B, Tmax, sd) and y.dtype == torch.float32 and y.device.type == device
+            (y * w.to(device) * mask.to(device)).sum().backward()
+            for b, n in enumerate(lens):
+                mb = means[b, :n].to(device).requires_grad_(True)
+                vb = v if gvar else v[b, :n]
+                yb = AF.mlpg(mb, vb, ws)
+                (yb * w[b, :n].to(device)).sum().backward()
+                assert torch.allclose(y[b, :n], yb, rtol=1e-6, atol=1e-6)
+                assert torch.allclose(m.grad[b, :n], mb.grad, rtol=1e-5, atol=1e-6)
+                assert not y[b, n:].any() and not m.grad[b, n:].any()
+    # flat (sum_T, D) form
+    flat = torch.cat([means[b, :n] for b, n in enumerate(lens)]).cuda().requires_grad_(True)
+    fv = torch.cat([var[b, :n] for b, n in enumerate(lens)]).cuda()
+    yf = AF.mlpg_batch(flat, fv, ws, lens)
+    yp = AF.mlpg_batch(means.cuda(), var.cuda(), ws, lens)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for b, n in enumerate(lens):
+        assert torch.equal(yf[off[b]:off[b + 1]], yp[b, :n])
