@@ -323,3 +323,28 @@ def test_ragged_batch_cfg5_shape():
         a, b = off[u], off[u + 1]
         assert rel_err(y[a:b], _oracle_merlin(m[a:b], v[a:b], ws, lens[u:u + 1])) < TOL32
     assert np.array_equal(y[:, 61], m[:, 183])
+
+
+def test_mlpg_grad_batch_merlin_layout():
+    """Batched gradient through the 187-column layout (three smoothed streams + the copied vuv column)."""
+    import torch
+    G = _G()
+    ws = windows_set()[2]
+    lay = G.merlin_layout()
+    for global_var in (False, True):
+        lens, m, v = _merlin_batch(7, 1, 150, 31, global_var)
+        n = m.shape[0]
+        go = np.random.default_rng(4).standard_normal((n, 63)).astype(np.float32)
+        got = G.mlpg_grad_batch(torch.from_numpy(v).cuda(), ws, torch.from_numpy(go).cuda(), lens, layout=lay).cpu().numpy()
+        assert got.shape == (n, 187) and got.dtype == np.float32
+        off = np.concatenate([[0], np.cumsum(lens)])
+        want = np.zeros((n, 187), np.float32)
+        for u in range(len(lens)):
+            a, b = off[u], off[u + 1]
+            z = np.zeros((b - a, 180), np.float32)
+            vv = (lambda c0, c1: v[c0:c1]) if v.ndim == 1 else (lambda c0, c1: v[a:b, c0:c1])
+            want[a:b, 0:180] = oracle.mlpg_grad(z, vv(0, 180), ws, go[a:b, 0:60])
+            want[a:b, 180:183] = oracle.mlpg_grad(z[:, :3], vv(180, 183), ws, go[a:b, 60:61])
+            want[a:b, 183] = go[a:b, 61]
+            want[a:b, 184:187] = oracle.mlpg_grad(z[:, :3], vv(184, 187), ws, go[a:b, 62:63])
+        assert rel_err(got, want) < 2e-6, global_var
