@@ -48,7 +48,6 @@ struct DtwParams {
   int smem_bp_cap;  // bytes of back-pointer space available in shared memory (fast mode)
   size_t cost_cap;  // doubles of per-pair cost buffer (fast mode)
   unsigned long long* prof;  // optional [8] cycle counters (NNK_DTW_PROF=1): build, window, cost, wavefront, backtrack
-  int debug_skip;   // NNK_DTW_SKIP bitmask for phase timing experiments (1 = cost phase, 2 = wavefront, 4 = backtrack)
   double logdb;
 };
 
@@ -272,7 +271,7 @@ __global__ void __launch_bounds__(FD_BLOCK) fastdtw_kernel(const DtwParams p) {
     // lane l of a group accumulates the strided partial sum r_l of numpy's pairwise reduction (elements
     // l, l+8, l+16, ...); a three-step butterfly combines r_0..r_7 in exactly numpy's association
     // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); lane 0 adds the tail and takes the square root.
-    if (fast_d && !(p.debug_skip & 1)) {
+    if (fast_d) {
       const int grp = tid >> 3, gl = tid & 7;  // 16 groups of 8 lanes
       const int n8 = D - (D % 8), ntail = D - n8;
       const bool batched = (D >= 8 && D <= 32);  // <= 4 strided elements per lane: one batch of loads per cell
@@ -347,7 +346,7 @@ __global__ void __launch_bounds__(FD_BLOCK) fastdtw_kernel(const DtwParams p) {
 
     FD_TICK(2);
     const int ndiag = Tx + Ty - 1;
-    if (warp == 0 && fast_d && !(p.debug_skip & 2)) {
+    if (warp == 0 && fast_d) {
       // ---- (D) wavefront, one lane per active row -------------------------------------------------
       int imin = 0, imax = -1;
       int r_lo = 0, r_hi = 0, r_off = 0, p_lo = 0, p_hi = 0;  // my row's window / offset, previous row's window
@@ -446,7 +445,7 @@ __global__ void __launch_bounds__(FD_BLOCK) fastdtw_kernel(const DtwParams p) {
       bool ok = true;
       int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
       int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
-      while (i >= 0 && j >= 0 && !(p.debug_skip & 4)) {
+      while (i >= 0 && j >= 0) {
         if (j < lo[i] || j >= hi[i]) { ok = false; break; }
         if (lev == 0) {
           if (n >= p.path_ld) { ok = false; break; }
@@ -908,7 +907,6 @@ extern "C" int nnk_dtw_align(const nnk_dtw_args_t* a, void* stream) {
     }
     p.smem_bp_cap = (int)bound;
     p.cost_cap = dtw_fast_cells_bound(a->max_tx, a->max_ty, a->radius);
-    { const char* e = getenv("NNK_DTW_SKIP"); p.debug_skip = e ? atoi(e) : 0; }
     static unsigned long long* d_prof = nullptr;
     p.prof = nullptr;
     if (getenv("NNK_DTW_PROF")) {
