@@ -88,16 +88,16 @@ struct TmaGeom {
   uint32_t sb_ws;  // bytes of one scratch stage
 };
 
-// reciprocal of a positive, normal double: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps.
-// Not correctly rounded (<= 1 ulp); the pivots it inverts are only used inside the factorisation.
+// reciprocal of a positive, normal double: hardware seed (MUFU.RCP64H, relative error e ~ 2^-20) and
+// one cubic correction x (1 + e + e^2): error ~ e^3 < 2^-53, three dependent FMAs on the loop-carried
+// chain of the elimination instead of the four of two Newton steps.  Not correctly rounded (<= 1 ulp);
+// the pivots it inverts are only used inside the factorisation.
 __device__ __forceinline__ double rcp_pos(double d) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  double e = fma(-d, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-d, x, 1.0);
-  x = fma(x, e, x);
-  return x;
+  const double e = fma(-d, x, 1.0);
+  const double t = fma(e, e, e);
+  return fma(x, t, x);
 }
 
 // 1 / v in the INPUT dtype like the reference (paramgen/_mlpg.py:188).  float: MUFU.RCP + one
