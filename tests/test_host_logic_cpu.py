@@ -1,0 +1,61 @@
+"""Host-side logic that needs no GPU: stream layouts, the GMM parameter split of baseline.gmm
+(against the live reference when oracle/_ref is present), metric front-ends failing loudly."""
+import types
+
+import numpy as np
+import pytest
+
+import oracle
+
+
+def test_merlin_layout_chain_table():
+    from nnmnkwii_b200 import paramgen as G
+    lay = G.merlin_layout()
+    assert (lay.D_in, lay.D_out, lay.n_chain) == (187, 63, 63)
+    ch = lay.chains
+    assert list(ch["in_col"][:60]) == list(range(60)) and set(ch["win_stride"][:60]) == {60}
+    assert (ch["in_col"][60], ch["win_stride"][60], ch["out_col"][60], ch["flags"][60]) == (180, 1, 60, 0)
+    assert (ch["in_col"][61], ch["out_col"][61], ch["flags"][61]) == (183, 61, 1)  # vuv: copied
+    assert (ch["in_col"][62], ch["win_stride"][62], ch["out_col"][62], ch["flags"][62]) == (184, 1, 62, 0)
+    one = G.StreamLayout.single(177, 3)  # static_dim = D // num_windows (_mlpg.py:172)
+    assert (one.D_out, one.n_chain) == (59, 59) and set(one.chains["win_stride"]) == {59}
+
+
+def _random_gmm(seed=0, M=3, dim=4):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((M, 2 * dim, 2 * dim))
+    cov = A @ A.transpose(0, 2, 1) + 0.5 * np.eye(2 * dim)
+    w = rng.random(M) + 0.1
+    return types.SimpleNamespace(means_=rng.standard_normal((M, 2 * dim)), covariances_=cov, weights_=w / w.sum(),
+                                 covariance_type="full")
+
+
+@pytest.mark.parametrize("swap,diff", [(False, False), (True, False), (False, True), (True, True)])
+def test_gmm_parameter_split_matches_reference(swap, diff):
+    if not oracle.reference_available():
+        pytest.skip("oracle/_ref not built")
+    oracle.import_reference()
+    from nnmnkwii.baseline.gmm import MLPGBase as Ref
+    from nnmnkwii_b200.baseline.gmm import MLPG, MLPGBase
+    gmm = _random_gmm()
+    ours, ref = MLPGBase(gmm, swap=swap, diff=diff), Ref(gmm, swap=swap, diff=diff)
+    for name in ("src_means", "tgt_means", "covarXX", "covarXY", "covarYX", "covarYY", "weights"):
+        assert np.array_equal(getattr(ours, name), getattr(ref, name)), name
+    assert ours.num_mixtures == ref.num_mixtures
+    assert np.allclose(ours._prec_chol, ref.px.precisions_cholesky_, rtol=1e-12, atol=1e-14)
+    m = MLPG(gmm)  # default windows: static + delta (gmm.py:199-203)
+    assert len(m.windows) == 2 and m.static_dim == 2
+
+
+def test_metric_front_ends_fail_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from nnmnkwii_b200 import metrics as M
+    from nnmnkwii_b200.baseline.gmm import MLPGBase
+    x = np.zeros((3, 4), np.float32)
+    for call in (lambda: M.melcd(x, x), lambda: M.mean_squared_error(x, x, [3]), lambda: M.vuv_error(x[:, 0], x[:, 0]),
+                 lambda: MLPGBase(_random_gmm()).transform(np.zeros((2, 4)))):
+        with pytest.raises(RuntimeError) as ei:
+            call()
+        assert "CUDA" in str(ei.value)
