@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NNK_ABI_VERSION 1
+#define NNK_ABI_VERSION 2
 
 #define NNK_OK 0
 #define NNK_ERR_ARG -1          /* bad argument                                               */
@@ -102,6 +102,9 @@ typedef struct nnk_mlpg_args {
   void* workspace;            /* device scratch, >= nnk_mlpg_workspace_bytes()                 */
   size_t workspace_bytes;
   uint64_t* status_word;      /* device; must be zeroed by the caller before the first launch  */
+  const int64_t* out_off;     /* device (n_utt) first OUTPUT row of every utterance, or NULL =>
+                                 utt_off (same rows in and out).  Lets a rank write its slice of
+                                 a sharded batch straight into its slot of the all-gather buffer */
 } nnk_mlpg_args_t;
 
 void nnk_status_decode(uint64_t status_word, nnk_status_t* out);
@@ -226,6 +229,16 @@ int nnk_f0_metric(const void* src_f0, const void* src_vuv, const void* tgt_f0, c
                   int32_t B, int32_t T, int64_t item_stride, int64_t frame_stride, const int32_t* lengths,
                   int32_t kind, double* sum_out, int64_t* count_out, void* workspace, int64_t workspace_bytes,
                   void* stream);
+
+/* ---- sharded batches (the reference has no multi-device path) ------------------------
+ * Copies n_seg row segments (whole utterances) between two row-major device matrices:
+ * dst[dst_row[s] + r, 0:cols] = src[src_row[s] + r, 0:cols] for r < len[s].  Used to bring the
+ * all-gathered trajectories (shard order: bucket, rank, utterance) back into the caller's utterance
+ * order, i.e. the order the reference's per-utterance loop over paramgen.mlpg
+ * (paramgen/_mlpg.py:92) would have produced them in.  elem_bytes 4 or 8; n_seg <= 65535 per call. */
+int nnk_segment_copy(const void* src, void* dst, int32_t elem_bytes, int64_t cols, int64_t src_ld, int64_t dst_ld,
+                     const int64_t* src_row, const int64_t* dst_row, const int32_t* len, int32_t n_seg,
+                     int32_t max_len, void* stream);
 
 const char* nnk_last_error(void);
 int nnk_abi_version(void);

@@ -15,7 +15,7 @@ NNK_OK, NNK_ERR_ARG, NNK_ERR_UNSUPPORTED, NNK_ERR_CUDA, NNK_ERR_WORKSPACE, NNK_E
 NNK_F32, NNK_F64 = 0, 1
 NNK_MAX_WIN, NNK_MAX_HALF = 4, 4
 NNK_MAX_TAPS = 2 * NNK_MAX_HALF + 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class NnkWindows(ctypes.Structure):
@@ -54,6 +54,7 @@ class NnkMlpgArgs(ctypes.Structure):
         ("workspace", ctypes.c_void_p),
         ("workspace_bytes", ctypes.c_size_t),
         ("status_word", ctypes.c_void_p),
+        ("out_off", ctypes.c_void_p),
     ]
 
 
@@ -94,7 +95,7 @@ EXPORTS = [
     "nnk_mlpg_fwd", "nnk_mlpg_grad", "nnk_mlpg_solve", "nnk_mlpg_workspace_bytes", "nnk_mlpg_host", "nnk_mlpg_batch_host",
     "nnk_uv_band_profile", "nnk_uv_band_extract", "nnk_uv_apply", "nnk_uv_apply_toeplitz",
     "nnk_dtw_align", "nnk_dtw_workspace_bytes", "nnk_gather_rows", "nnk_trim_lengths", "nnk_delta_features",
-    "nnk_metric_workspace_bytes", "nnk_frame_metric", "nnk_f0_metric",
+    "nnk_metric_workspace_bytes", "nnk_frame_metric", "nnk_f0_metric", "nnk_segment_copy",
 ]
 
 
@@ -153,6 +154,8 @@ def _load():
     L.nnk_frame_metric.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, i64, vp]
     L.nnk_f0_metric.restype = ctypes.c_int
     L.nnk_f0_metric.argtypes = [vp, vp, vp, vp, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, i64, vp]
+    L.nnk_segment_copy.restype = ctypes.c_int
+    L.nnk_segment_copy.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, vp, i32, i32, vp]
     return L
 
 

@@ -23,6 +23,14 @@ def _cuda_device(t):
     return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
 
 
+def _global_variance(variances):
+    """A global ``(D,)`` variance -- given as such or as ``v.expand(T, D)`` (stride 0 over frames, what
+    the reference's ``autograd.mlpg`` builds, mlpg.py:196-197) -- as a 1-D tensor; anything else unchanged."""
+    if variances.dim() == 2 and variances.shape[0] > 1 and variances.stride(0) == 0:
+        return variances[0]
+    return variances
+
+
 class MLPG(Function):
     """Generic MLPG as an autograd function, ``f : (T, D) -> (T, static_dim)`` (mlpg.py:8-67).
 
@@ -34,12 +42,16 @@ class MLPG(Function):
     def forward(ctx, means, variances, windows):
         assert means.dim() == 2  # we cannot do MLPG on minibatch (mlpg.py:44)
         ctx.windows = windows
+        variances = _global_variance(variances)  # (D,) or a stride-0 expansion of it -> 1-D (16*sd B/frame path)
         ctx.save_for_backward(means, variances)
-        assert means.size() == variances.size()
+        assert variances.dim() == 1 or means.size() == variances.size()
         device = _cuda_device(means)
         m = means.detach().to(device)
         v = variances.detach().to(device)
-        y = G.mlpg(m, v, windows).to(torch.float32)
+        # CUDA inputs: non-blocking status check (surfaces at the next call); CPU inputs (the reference's
+        # use) synchronise on the copy back anyway, so the check is immediate
+        ctx.check = "deferred" if means.is_cuda else True
+        y = G.mlpg_batch(m, v, windows, lengths=[m.shape[0]], check=ctx.check).to(torch.float32)
         return y.to(means.device)
 
     @staticmethod
@@ -47,7 +59,7 @@ class MLPG(Function):
         means, variances = ctx.saved_tensors
         device = _cuda_device(means)
         g = G.mlpg_grad(means.detach().to(device), variances.detach().to(device), ctx.windows,
-                        grad_output.detach().to(device))
+                        grad_output.detach().to(device), check=ctx.check)
         return g.to(means.device), None, None
 
 
@@ -64,14 +76,17 @@ class MLPGBatch(Function):
         ctx.lengths = [int(n) for n in (lengths.tolist() if torch.is_tensor(lengths) else lengths)]
         ctx.save_for_backward(means, variances)
         device = _cuda_device(means)
-        y = G.mlpg_batch(means.detach().to(device), variances.detach().to(device), windows, lengths=ctx.lengths)
+        ctx.check = "deferred" if means.is_cuda else True
+        y = G.mlpg_batch(means.detach().to(device), variances.detach().to(device), windows, lengths=ctx.lengths,
+                         check=ctx.check)
         return y.to(torch.float32).to(means.device)
 
     @staticmethod
     def backward(ctx, grad_output):
         means, variances = ctx.saved_tensors
         device = _cuda_device(means)
-        g = G.mlpg_grad_batch(variances.detach().to(device), ctx.windows, grad_output.detach().to(device), ctx.lengths)
+        g = G.mlpg_grad_batch(variances.detach().to(device), ctx.windows, grad_output.detach().to(device), ctx.lengths,
+                              check=ctx.check)
         return g.to(means.device), None, None, None
 
 
@@ -133,9 +148,8 @@ def mlpg(means, variances, windows):
     ``variances`` may be ``(T, D)`` or global ``(D,)`` (expanded over frames).
     """
     T, D = means.size()
-    if variances.dim() == 1 and variances.shape[0] == D:
-        variances = variances.expand(T, D)
-    assert means.size() == variances.size()
+    if not (variances.dim() == 1 and variances.shape[0] == D):  # a global (D,) variance stays 1-D
+        assert means.size() == variances.size()
     return MLPG.apply(means, variances, windows)
 
 

@@ -29,6 +29,31 @@ void count_launch(int n = 1);
     }                                                   \
   } while (0)
 
+// ---- device guard ---------------------------------------------------------------------------
+// Every launching entry point runs on the device that OWNS the data it was given, not on whatever
+// device happens to be current in the calling thread (torch's default stream handle 0 is valid on
+// every device, so a launch with cuda:1 pointers while cuda:0 is current would otherwise run on the
+// wrong GPU or fault).  The previous device is restored on return.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void* device_ptr) {
+    cudaPointerAttributes at;
+    if (device_ptr && cudaPointerGetAttributes(&at, device_ptr) == cudaSuccess &&
+        (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+      dev = at.device;
+      if (cudaGetDevice(&prev) == cudaSuccess && prev != dev && cudaSetDevice(dev) == cudaSuccess) switched = true;
+    } else {
+      cudaGetLastError();  // not a device pointer: leave the current device alone
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // ---- status key ------------------------------------------------------------------------------
 // The device keeps ONE 64-bit word: 0 = ok, otherwise ~((utt << 42) | (chain << 21) | frame) of the
 // lexicographically FIRST failure (utterance, then chain, then frame) -- the order in which the

@@ -58,6 +58,7 @@ extern "C" int nnk_delta_features(const void* x, int32_t dtype, int32_t D, int64
   NNK_REQUIRE(D >= 0 && n_utt >= 0 && max_T >= 0, NNK_ERR_ARG, "bad size");
   if (D == 0 || n_utt == 0 || max_T == 0) return NNK_OK;
   NNK_REQUIRE(n_utt <= 65535 && (D + 31) / 32 <= 65535, NNK_ERR_ARG, "too many utterances / dims for one launch");
+  DeviceGuard guard(x);
   DeltaParams p;
   p.x = x; p.out = out; p.x_ld = x_ld; p.out_ld = out_ld; p.utt_off = utt_off; p.utt_len = utt_len; p.D = D; p.win = *win;
   dim3 grid((unsigned)((max_T + 7) / 8), (unsigned)((D + 31) / 32), (unsigned)n_utt), block(32, 8);

@@ -828,6 +828,7 @@ extern "C" int nnk_dtw_align(const nnk_dtw_args_t* a, void* stream) {
   NNK_REQUIRE(a->cost_kind == 0 || a->cost_kind == 1, NNK_ERR_UNSUPPORTED, "cost_kind must be 0 (euclid) or 1 (melcd)");
   NNK_REQUIRE(a->path_ld >= a->max_tx + a->max_ty - 1, NNK_ERR_ARG, "path_ld < max_tx + max_ty - 1");
   NNK_REQUIRE(a->radius != 0, NNK_ERR_UNSUPPORTED, "radius 0 is not supported (fastdtw itself fails on odd lengths)");
+  DeviceGuard guard(a->X);
   cudaStream_t st = (cudaStream_t)stream;
   const bool full = a->radius < 0;
   const int mt = a->max_tx > a->max_ty ? a->max_tx : a->max_ty;
@@ -934,6 +935,7 @@ extern "C" int nnk_gather_rows(const void* X, int32_t dtype, int64_t x_pair_stri
                                int32_t out_rows, int32_t D, int32_t n_pairs, void* stream) {
   NNK_REQUIRE(X && path && path_len && out, NNK_ERR_ARG, "NULL pointer");
   if (n_pairs == 0 || out_rows == 0 || D == 0) return NNK_OK;
+  DeviceGuard guard(X);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)(((int64_t)out_rows * D + 255) / 256), (unsigned)n_pairs);
   if (grid.x > 1024) grid.x = 1024;
@@ -950,6 +952,7 @@ extern "C" int nnk_trim_lengths(const void* X, int32_t dtype, int64_t pair_strid
                                 double eps, int32_t n_pairs, int32_t* len, void* stream) {
   NNK_REQUIRE(X && len, NNK_ERR_ARG, "NULL pointer");
   if (n_pairs == 0) return NNK_OK;
+  DeviceGuard guard(X);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == NNK_F32) trim_len_kernel<float><<<n_pairs, 128, 0, st>>>((const float*)X, pair_stride, ld, T, D, (float)eps, len);
   else trim_len_kernel<double><<<n_pairs, 128, 0, st>>>((const double*)X, pair_stride, ld, T, D, eps, len);

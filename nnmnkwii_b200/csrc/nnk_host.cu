@@ -55,7 +55,10 @@ struct HostCtx {
     return NNK_OK;
   }
 };
-static HostCtx g_ctx;
+// one context (arena + streams) per device: the streams and allocations of a context belong to the
+// device that was current when it was first used
+static constexpr int kMaxDevices = 64;
+static HostCtx g_ctx_by_device[kMaxDevices];
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -75,6 +78,10 @@ extern "C" int nnk_mlpg_batch_host(const void* means, const void* vars, int32_t 
   NNK_REQUIRE(utt_off[0] == 0 && utt_off[n_utt] == n_rows, NNK_ERR_ARG, "utt_off must span [0, n_rows]");
   const size_t es = dtype == NNK_F32 ? 4 : 8;
 
+  int device = 0;
+  NNK_CUDA_CHECK(cudaGetDevice(&device));
+  NNK_REQUIRE(device >= 0 && device < kMaxDevices, NNK_ERR_ARG, "device index out of range");
+  HostCtx& g_ctx = g_ctx_by_device[device];
   std::lock_guard<std::mutex> lock(g_ctx.mu);
   int rc = g_ctx.init();
   if (rc) return rc;

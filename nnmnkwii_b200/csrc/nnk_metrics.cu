@@ -362,6 +362,7 @@ extern "C" int nnk_frame_metric(const void* X, const void* Y, int32_t dtype, int
                                 double* sum_out, int64_t* count_out, void* workspace, int64_t workspace_bytes,
                                 void* stream) {
   NNK_REQUIRE(sum_out && count_out, NNK_ERR_ARG, "NULL output");
+  DeviceGuard guard(sum_out);
   NNK_REQUIRE(dtype == NNK_F32 || dtype == NNK_F64, NNK_ERR_ARG, "bad dtype");
   NNK_REQUIRE(kind == 0 || kind == 1, NNK_ERR_ARG, "bad kind");
   NNK_REQUIRE(B >= 0 && T >= 0 && D >= 0 && T <= (1 << 30), NNK_ERR_ARG, "bad size");
@@ -390,6 +391,7 @@ extern "C" int nnk_f0_metric(const void* src_f0, const void* src_vuv, const void
                              const int32_t* lengths, int32_t kind, double* sum_out, int64_t* count_out,
                              void* workspace, int64_t workspace_bytes, void* stream) {
   NNK_REQUIRE(sum_out && count_out, NNK_ERR_ARG, "NULL output");
+  DeviceGuard guard(sum_out);
   NNK_REQUIRE(dtype == NNK_F32 || dtype == NNK_F64, NNK_ERR_ARG, "bad dtype");
   NNK_REQUIRE(kind >= 0 && kind <= 2, NNK_ERR_ARG, "bad kind");
   NNK_REQUIRE(B >= 0 && T >= 0 && T <= (1 << 30), NNK_ERR_ARG, "bad size");

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(32) mlpg_kernel(const __grid_constant__ MlpgPa
   const int64_t row0 = p.utt_off[utt];
   const int T = p.utt_len ? p.utt_len[utt] : (int)(p.utt_off[utt + 1] - row0);
   if (T <= 0) return;
+  const int64_t orow0 = p.out_off ? p.out_off[utt] : row0;
   const int chain = grp * 32 + lane;
   const bool active = chain < p.n_chain;
   nnk_chain_t ch;
@@ -66,10 +67,10 @@ __global__ void __launch_bounds__(32) mlpg_kernel(const __grid_constant__ MlpgPa
   // ---- pass-through chains (flags & 1): plain copy (fwd) / gradient of a copy (grad) -----------
   if (active && (ch.flags & 1)) {
     if (MODE == MODE_FWD) {
-      Tin* o = reinterpret_cast<Tin*>(p.out) + row0 * p.out_ld + ch.out_col;
+      Tin* o = reinterpret_cast<Tin*>(p.out) + orow0 * p.out_ld + ch.out_col;
       for (int t = 0; t < T; ++t) o[(int64_t)t * p.out_ld] = mptr[(int64_t)t * p.in_ld];
     } else if (MODE == MODE_GRAD) {
-      float* o = reinterpret_cast<float*>(p.out) + row0 * p.out_ld + ch.in_col;
+      float* o = reinterpret_cast<float*>(p.out) + orow0 * p.out_ld + ch.in_col;
       for (int t = 0; t < T; ++t) o[(int64_t)t * p.out_ld] = (float)load_go(p.go, p.go_f64, (row0 + t) * p.go_ld + chain);
     }
   }
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(32) mlpg_kernel(const __grid_constant__ MlpgPa
         yw[0] = y;
         load_ws(t - PF, rz[jj], rl[jj]);
         if (MODE != MODE_GRAD) {
-          if (solve) st_stream(reinterpret_cast<Tin*>(p.out) + (row0 + t) * p.out_ld + ch.out_col, (Tin)y);
+          if (solve) st_stream(reinterpret_cast<Tin*>(p.out) + (orow0 + t) * p.out_ld + ch.out_col, (Tin)y);
         } else {
           // row r = t + L of the gradient: tau_w[r] * sum_k c[w][L+k] x[r+k],  x[r+k] = yw[L+k]
           const int r = t + L;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(32) mlpg_kernel(const __grid_constant__ MlpgPa
                 double s = 0.0;
 #pragma unroll
                 for (int i = 0; i < NT; ++i) s = fma(p.win.c[w][i], yw[i], s);  // c[w][L+k], k = i-L
-                reinterpret_cast<float*>(p.out)[(row0 + r) * p.out_ld + ch.in_col + w * ch.win_stride] =
+                reinterpret_cast<float*>(p.out)[(orow0 + r) * p.out_ld + ch.in_col + w * ch.win_stride] =
                     (float)(tau[w] * s);
               }
             }
@@ -353,7 +354,7 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   if (!fill_wintab<NW, L, U>(a.win, p.win)) { set_error("window set does not fit kernel instance"); return NNK_ERR_UNSUPPORTED; }
   p.means = (const Tin*)a.means; p.vars = (const Tin*)a.vars; p.go = a.grad_out; p.go_f64 = a.go_f64; p.out = a.out;
   p.in_ld = a.in_ld; p.var_ld = a.var_ld; p.go_ld = a.go_ld; p.out_ld = a.out_ld;
-  p.utt_off = a.utt_off; p.utt_len = a.utt_len; p.order = a.order; p.chains = a.chains;
+  p.utt_off = a.utt_off; p.out_off = a.out_off; p.utt_len = a.utt_len; p.order = a.order; p.chains = a.chains;
   p.n_utt = a.n_utt; p.n_chain = a.n_chain; p.n_groups = (a.n_chain + 31) / 32; p.max_T = a.max_T;
   p.ws = (double*)a.workspace; p.status = (unsigned long long*)a.status_word;
   const size_t per_item = (size_t)a.max_T * NT * 32 * sizeof(double);
@@ -472,6 +473,7 @@ extern "C" int nnk_mlpg_fwd(const nnk_mlpg_args_t* a, void* stream) {
   int r = check_args(a, false);
   if (r < 0) return r;
   if (r > 0) return NNK_OK;
+  DeviceGuard guard(a->out);
   cudaStream_t st = (cudaStream_t)stream;
   return a->dtype == NNK_F32 ? dispatch_inst<float, MODE_FWD>(*a, st) : dispatch_inst<double, MODE_FWD>(*a, st);
 }
@@ -480,6 +482,7 @@ extern "C" int nnk_mlpg_solve(const nnk_mlpg_args_t* a, void* stream) {
   int r = check_args(a, true);
   if (r < 0) return r;
   if (r > 0) return NNK_OK;
+  DeviceGuard guard(a->out);
   cudaStream_t st = (cudaStream_t)stream;
   return a->dtype == NNK_F32 ? dispatch_inst<float, MODE_SOLVE>(*a, st) : dispatch_inst<double, MODE_SOLVE>(*a, st);
 }
@@ -488,6 +491,7 @@ extern "C" int nnk_mlpg_grad(const nnk_mlpg_args_t* a, void* stream) {
   int r = check_args(a, true);
   if (r < 0) return r;
   if (r > 0) return NNK_OK;
+  DeviceGuard guard(a->out);
   cudaStream_t st = (cudaStream_t)stream;
   return a->dtype == NNK_F32 ? dispatch_inst<float, MODE_GRAD>(*a, st) : dispatch_inst<double, MODE_GRAD>(*a, st);
 }

@@ -26,6 +26,7 @@ struct MlpgParams {
   void* out;
   int64_t in_ld, var_ld, go_ld, out_ld;
   const int64_t* utt_off;
+  const int64_t* out_off;  // first output row per utterance (NULL: utt_off)
   const int32_t* utt_len;
   const int32_t* order;
   const nnk_chain_t* chains;

@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   __syncthreads();
 
   const int npb = (T + L + TT - 1) / TT;  // band-row tiles: tile k holds rows r = k*TT - L + j, j < TT
-  Tin* const outp = reinterpret_cast<Tin*>(p.out) + row0 * p.out_ld + ch.out_col;
-  float* const outg = reinterpret_cast<float*>(p.out) + row0 * p.out_ld + ch.in_col;  // GRAD: (T, D) float32
+  const int64_t orow0 = p.out_off ? p.out_off[utt] : row0;
+  Tin* const outp = reinterpret_cast<Tin*>(p.out) + orow0 * p.out_ld + ch.out_col;
+  float* const outg = reinterpret_cast<float*>(p.out) + orow0 * p.out_ld + ch.in_col;  // GRAD: (T, D) float32
 
   // column span [cmin, cmax] of the variance (and means) rows this group touches
   const int lo_c = active ? ch.in_col : INT_MAX;

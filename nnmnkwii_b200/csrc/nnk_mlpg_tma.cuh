@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(32) mlpg_fwd_tma_kernel(const __grid_constant_
 
   double* const ws0 = p.ws + (size_t)item * ((size_t)p.max_T * NT * 32);
   double* wsp = ws0 + lane;
-  Tin* const outp = reinterpret_cast<Tin*>(p.out) + row0 * p.out_ld + ch.out_col;
+  const int64_t orow0 = p.out_off ? p.out_off[utt] : row0;
+  Tin* const outp = reinterpret_cast<Tin*>(p.out) + orow0 * p.out_ld + ch.out_col;
 
   // ---- forward sweep ---------------------------------------------------------------------------
   double vcol[S + 1][S + 1], lcol[S + 1][S + 1], zz[S + 1];

@@ -348,6 +348,7 @@ using namespace nnk;
 
 extern "C" int nnk_uv_band_profile(const void* R, int32_t dtype, int32_t T, int32_t nw, float* profile, void* stream) {
   NNK_REQUIRE(R && profile && T > 0 && nw > 0, NNK_ERR_ARG, "bad argument");
+  DeviceGuard guard(R);
   cudaStream_t st = (cudaStream_t)stream;
   NNK_CUDA_CHECK(cudaMemsetAsync(profile, 0, sizeof(float) * (size_t)T, st));
   if (dtype == NNK_F32) uv_profile_kernel<float><<<T, 256, 0, st>>>((const float*)R, T, nw, profile);
@@ -360,6 +361,7 @@ extern "C" int nnk_uv_band_profile(const void* R, int32_t dtype, int32_t T, int3
 extern "C" int nnk_uv_band_extract(const void* R, int32_t dtype, int32_t T, int32_t nw, int32_t K, void* Rb, void* RbT,
                                    void* stream) {
   NNK_REQUIRE(R && Rb && RbT && T > 0 && nw > 0 && K >= 0, NNK_ERR_ARG, "bad argument");
+  DeviceGuard guard(R);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == NNK_F32) uv_extract_kernel<float><<<T, 128, 0, st>>>((const float*)R, T, nw, K, (float*)Rb, (float*)RbT);
   else uv_extract_kernel<double><<<T, 128, 0, st>>>((const double*)R, T, nw, K, (double*)Rb, (double*)RbT);
@@ -373,6 +375,7 @@ extern "C" int nnk_uv_apply(const void* table, const void* x, void* y, int32_t d
   NNK_REQUIRE(table && x && y, NNK_ERR_ARG, "NULL pointer");
   NNK_REQUIRE(B >= 0 && T > 0 && sd >= 0 && nw > 0 && K >= 0, NNK_ERR_ARG, "bad size");
   if (B == 0 || sd == 0) return NNK_OK;
+  DeviceGuard guard(x);
   cudaStream_t st = (cudaStream_t)stream;
   return dtype == NNK_F32 ? uv_apply<float>(table, x, y, B, T, sd, nw, K, backward, reshaped, 0, 0, st)
                           : uv_apply<double>(table, x, y, B, T, sd, nw, K, backward, reshaped, 0, 0, st);
@@ -389,6 +392,7 @@ extern "C" int nnk_uv_apply_toeplitz(const void* table, const float* taps, const
   NNK_REQUIRE(B >= 0 && T > 0 && sd >= 0 && nw > 0 && K >= 0 && t_lo >= 0 && t_hi <= T && t_lo <= t_hi, NNK_ERR_ARG, "bad size");
   if (B == 0 || sd == 0) return NNK_OK;
   NNK_REQUIRE(B <= 65535 && (sd + 31) / 32 <= 65535, NNK_ERR_ARG, "batch or static_dim too large for one launch");
+  DeviceGuard guard(x);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = uv_apply<float>(table, x, y, B, T, sd, nw, K, backward, reshaped, t_lo, t_hi, st);
   if (rc || t_hi == t_lo) return rc;

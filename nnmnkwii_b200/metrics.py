@@ -64,10 +64,14 @@ def _reduce(call, device, B, T):
     from . import _device as dev
     from ._lib import check, lib
     need = int(lib.nnk_metric_workspace_bytes(max(1, B), max(1, T)))
-    ws = _ws_cache.get(device)
+    # one ticketed partial buffer per (device, stream): reductions on different streams never share it
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.zeros(need, dtype=torch.uint8, device=device)  # zeroed once; every call leaves it reusable
-        _ws_cache[device] = ws
+        if len(_ws_cache) > 32:
+            _ws_cache.clear()
+        _ws_cache[key] = ws
     res = torch.zeros(2, dtype=torch.float64, device=device)  # [sum, count (int64 bits)]
     rc = call(ctypes.c_void_p(res.data_ptr()), ctypes.c_void_p(res.data_ptr() + 8),
               ctypes.c_void_p(ws.data_ptr()), ctypes.c_int64(ws.numel()), dev.current_stream_ptr(device))

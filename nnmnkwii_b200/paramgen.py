@@ -294,7 +294,7 @@ def mlpg(mean_frames, variance_frames, windows):
     return y if y.dtype == dtype else y.astype(dtype)
 
 
-def mlpg_grad(mean_frames, variance_frames, windows, grad_output):
+def mlpg_grad(mean_frames, variance_frames, windows, grad_output, check=True):
     r"""MLPG gradient (_mlpg.py:202-281): returns ``(T, D)`` float32,
 
     .. math:: g_{d,l} = P_{d,l} \, W_l (\sum_l W_l^T P_{d,l} W_l)^{-1} o_d
@@ -318,9 +318,10 @@ def mlpg_grad(mean_frames, variance_frames, windows, grad_output):
     v = to_dev(variance_frames)
     if v.dtype not in (torch.float32, torch.float64):
         v = v.to(torch.float64)
+    if v.dim() == 2 and v.shape[0] > 1 and v.stride(0) == 0:
+        v = v[0]  # v.expand(T, D) of a global variance (tests/test_autograd.py:191): keep it 1-D
     var1d = v.dim() == 1
-    if not var1d:
-        v = v.contiguous()  # materialises stride-0 expanded variances (tests/test_autograd.py:191)
+    v = v.contiguous()
     go = to_dev(grad_output)
     if go.dtype not in (torch.float32, torch.float64):
         go = go.to(torch.float32)
@@ -336,13 +337,13 @@ def mlpg_grad(mean_frames, variance_frames, windows, grad_output):
             chains=dev.chains_on_device(chains, device), n_chain=static_dim, max_T=T,
             windows_c=_lib.make_windows(windows), in_ld=D, var_ld=0 if var1d else D, go_ld=go.shape[1], out_ld=D,
             dtype_code=dev.torch_dtype_code(v.dtype), go_f64=int(go.dtype == torch.float64), n_utt=1,
-            device=device, check=True)
+            device=device, check=check)
     if is_t:
         return out
     return out.cpu().numpy()
 
 
-def mlpg_grad_batch(variances, windows, grad_output, lengths, layout=None):
+def mlpg_grad_batch(variances, windows, grad_output, lengths, layout=None, check=True):
     """Batched :func:`mlpg_grad` on the device (additive API): the gradients of
     ``mlpg_batch(means, variances, windows, lengths, layout=layout)`` with respect to ``means`` for
     every utterance of the batch in ONE launch of ``nnk_mlpg_grad``.
@@ -410,7 +411,7 @@ def mlpg_grad_batch(variances, windows, grad_output, lengths, layout=None):
             chains=dev.chains_on_device(layout.chains, device), n_chain=layout.n_chain, max_T=max_T,
             windows_c=_lib.make_windows(windows), in_ld=D, var_ld=0 if var1d else D, go_ld=layout.n_chain, out_ld=D,
             dtype_code=dev.torch_dtype_code(v.dtype), go_f64=int(go2.dtype == torch.float64), n_utt=n_utt,
-            device=device, check=True)
+            device=device, check=check)
     return out.reshape(go.shape[0], go.shape[1], D) if padded else out
 
 

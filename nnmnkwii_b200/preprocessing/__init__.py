@@ -10,25 +10,12 @@ def trim_zeros_frames(x, eps=1e-7, trim="b"):
     lengths on the device (C ABI ``nnk_trim_lengths``) without touching the host.
     """
     assert trim in {"f", "b", "fb"}
-    T, D = x.shape
-    s = np.sum(np.abs(x), axis=1)
-    s[s < eps] = 0.0
-    if trim == "f":
-        return x[len(x) - len(np.trim_zeros(s, trim=trim)):]
-    elif trim == "b":
-        end = len(np.trim_zeros(s, trim=trim)) - len(x)
-        if end == 0:
-            return x
-        else:
-            return x[:end]
-    elif trim == "fb":
-        f = len(np.trim_zeros(s, trim="f"))
-        b = len(np.trim_zeros(s, trim="b"))
-        end = b - len(x)
-        if end == 0:
-            return x[len(x) - f:]
-        else:
-            return x[len(x) - f: end]
+    live = np.flatnonzero(np.sum(np.abs(x), axis=1) >= eps)  # frames that are not (numerically) zero
+    if live.size == 0:
+        return x[:0] if len(x) else x
+    first = live[0] if "f" in trim else 0
+    last = live[-1] + 1 if "b" in trim else len(x)
+    return x if (first == 0 and last == len(x)) else x[first:last]
 
 
 def delta_features(x, windows, lengths=None):

@@ -10,7 +10,10 @@ sm_100a wavefront kernel (csrc/nnk_dtw.cu, one thread block per pair), followed 
 * the default ``lambda x, y: norm(x - y)``  -> Euclidean (``cost_kind`` 0)
 * ``melcd`` (this package's or the reference's ``nnmnkwii.metrics.melcd``) -> ``cost_kind`` 1
 
--- and any other callable raises ``NotImplementedError`` (no per-cell CPU fallback).
+-- by identity, by name (``"euclidean"`` / ``"melcd"``) or, for any other callable, by what it
+computes on a few probe frames (so the reference's own default lambda, or a user's re-spelling of it,
+is served natively); a callable that computes something else raises ``NotImplementedError`` (no
+per-cell CPU fallback).
 ``radius`` follows fastdtw (default 1); the additive ``radius=None`` / negative selects exact DTW.
 """
 import ctypes
@@ -19,6 +22,7 @@ import numpy as np
 from numpy.linalg import norm
 
 from .. import _lib
+from ..metrics import _logdb_const as _melcd_const
 from ..metrics import melcd as _melcd
 
 
@@ -26,17 +30,42 @@ def _default_dist(x, y):
     return norm(x - y)
 
 
+_PROBE = np.random.default_rng(20260923).standard_normal((6, 2, 13))
+
+
+def _probe_cost(dist):
+    """Which built-in local cost does a user callable compute?  It is evaluated on a handful of fixed
+    probe frames (host, once per aligner call, never per DP cell) and compared with the two costs
+    the kernel evaluates: returns 0 (Euclidean ``norm(x - y)``), 1 (``melcd``) or None."""
+    try:
+        got = np.array([float(dist(x, y)) for x, y in _PROBE])
+    except Exception:
+        return None
+    euclid = np.array([float(norm(x - y)) for x, y in _PROBE])
+    for kind, want in ((0, euclid), (1, _melcd_const * euclid)):
+        if np.allclose(got, want, rtol=1e-9, atol=0.0):
+            return kind
+    return None
+
+
 def _cost_kind(dist):
-    if dist is _default_dist or dist is None:
+    if dist is _default_dist or dist is None or dist == "euclidean":
         return 0
-    if dist is _melcd or (getattr(dist, "__name__", "") == "melcd" and "metrics" in getattr(dist, "__module__", "")):
+    if dist is _melcd or dist == "melcd" or (
+            getattr(dist, "__name__", "") == "melcd" and "metrics" in getattr(dist, "__module__", "")):
         return 1
     if dist is norm:
         raise NotImplementedError("dist must take two frames (x, y)")
+    # any callable that COMPUTES one of the two costs (e.g. the reference's own default
+    # ``lambda x, y: norm(x - y)``, alignment.py:35, or a user's re-spelling of it) is served natively
+    kind = _probe_cost(dist) if callable(dist) else None
+    if kind is not None:
+        return kind
     raise NotImplementedError(
-        "nnmnkwii_b200 DTW evaluates the local cost inside the CUDA kernel; supported `dist`: the default "
-        "Euclidean norm(x - y) and metrics.melcd. Arbitrary Python callables would need a per-cell CPU "
-        "callback, which this implementation does not provide.")
+        "nnmnkwii_b200 DTW evaluates the local cost inside the CUDA kernel; supported `dist`: callables that "
+        "compute the Euclidean norm(x - y) (the reference default) or metrics.melcd, or the names 'euclidean' / "
+        "'melcd'. Other Python callables would need a per-cell CPU callback, which this implementation does not "
+        "provide.")
 
 
 class _Aligned(object):

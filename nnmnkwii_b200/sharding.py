@@ -1,10 +1,23 @@
-"""Utterance sharding across the GPUs of one box.
+"""Utterance sharding across the GPUs of one box (BASELINE.json configs[4]).
 
-Every utterance (every DTW pair) is independent, so the data path has NO collective: the batch is
-partitioned by cost (frames) with a longest-first greedy rule, each rank runs the single-GPU path on
-its slice, and ONE all-gather at the end gives every rank the full result.  One process per GPU,
-``torch.distributed`` (NCCL over NVLink on the GPUs; gloo in the CPU tests) is only the plumbing.
+Every utterance is independent, so the data path has NO collective: the batch is dealt to ranks by
+cost (frames), each rank solves its slice with the single-GPU kernels, and the trajectories are
+all-gathered so that every rank ends up with the full result.  One process per GPU;
+``torch.distributed`` (NCCL over NVLink on the GPUs, gloo in the CPU tests) is only the plumbing.
+
+Layout (``ShardPlan``): the utterances are first dealt into ``n_buckets`` groups of equal frame
+count, and every group is split over the ranks by a longest-first greedy rule.  Bucket ``b`` of rank
+``r`` occupies rows ``[goff[b] + r * cap[b], ... + n[b][r])`` of ONE flat ``(rows_total, D_out)``
+result buffer (``cap[b]`` = largest per-rank frame count of the bucket, so the dead rows are at most
+one utterance per bucket and rank -- no per-utterance padding).  The MLPG kernel writes straight into
+that slot (``nnk_mlpg_args_t.out_off``) and the all-gather of bucket ``b`` is the in-place NCCL
+all-gather of the contiguous region ``[goff[b], goff[b] + world * cap[b])``.  The gather of bucket
+``b`` is issued on a side stream as soon as its solve has finished, so it overlaps the solve of
+bucket ``b + 1``; the result stays in shard order with a row table (``ShardedResult.row_start``) and
+is only re-ordered on request (``to_utterance_order``: one segment-copy kernel, no host indexing).
 """
+import ctypes
+
 import numpy as np
 
 
@@ -22,40 +35,233 @@ def partition(costs, world_size):
     return [np.array(sorted(b), dtype=np.int64) for b in buckets]
 
 
-def _flat_slice(lengths, idx):
-    off = np.concatenate([[0], np.cumsum(lengths)])
-    if len(idx) == 0:
-        return np.zeros(0, dtype=np.int64)
-    return np.concatenate([np.arange(off[i], off[i + 1]) for i in idx])
+class ShardPlan(object):
+    """Deterministic host-side plan (identical on every rank) of who solves what and where it lands.
+
+    Attributes:
+        members[b][r]: utterance ids (longest first) of bucket ``b`` on rank ``r``.
+        cap[b]:        rows reserved per rank in bucket ``b`` (max over ranks of the frame count).
+        goff[b]:       first row of bucket ``b`` in the gathered result; ``rows_total`` = its extent.
+        loff[b]:       first row of bucket ``b`` in a rank's LOCAL input buffers (``rows_local`` rows).
+        row_start[u]:  first row of utterance ``u`` in the gathered result (shard order).
+    """
+
+    def __init__(self, lengths, world_size, n_buckets=4):
+        self.lengths = np.asarray(lengths, dtype=np.int64)
+        self.world = int(world_size)
+        n = len(self.lengths)
+        nb = max(1, min(int(n_buckets), max(1, n // max(1, self.world))))
+        self.n_buckets = nb
+        # deal utterances (longest first) round-robin into buckets: equal frames and the same length mix
+        order = np.argsort(-self.lengths, kind="stable")
+        groups = [order[b::nb] for b in range(nb)]
+        self.members, self.cap, self.goff, self.loff = [], [], [], []
+        self.row_start = np.zeros(n, dtype=np.int64)
+        self.local_start = np.zeros(n, dtype=np.int64)
+        self.owner = np.zeros(n, dtype=np.int32)
+        g = l = 0
+        for b in range(nb):
+            parts = partition(self.lengths[groups[b]], self.world)
+            mem = []
+            for r in range(self.world):
+                ids = groups[b][parts[r]]
+                ids = ids[np.argsort(-self.lengths[ids], kind="stable")]
+                mem.append(ids)
+            cap = int(max((int(self.lengths[m].sum()) for m in mem), default=0))
+            self.members.append(mem)
+            self.cap.append(cap)
+            self.goff.append(g)
+            self.loff.append(l)
+            for r, ids in enumerate(mem):
+                o = 0
+                for u in ids:
+                    self.row_start[u] = g + r * cap + o
+                    self.local_start[u] = l + o
+                    self.owner[u] = r
+                    o += int(self.lengths[u])
+            g += self.world * cap
+            l += cap
+        self.rows_total = g
+        self.rows_local = l
+
+    def frames_of_rank(self, rank):
+        return int(sum(int(self.lengths[m[rank]].sum()) for m in self.members))
 
 
-def all_gather_rows(local, counts, group=None):
-    """All-gather a (n_local, D) tensor whose row count differs per rank (``counts[r]`` rows on rank
-    r).  One collective: the local block is padded to the largest count."""
+class ShardedBatch(object):
+    """One rank's slice of a sharded batch, resident on its GPU in plan layout: ``means`` /
+    ``variances`` ``(rows_local, D)`` (or a global ``(D,)`` variance), per-bucket launch metadata and
+    the flat gathered result buffer."""
+
+    def __init__(self, plan, rank, device, D_in, D_out, dtype):
+        import torch
+
+        self.plan, self.rank, self.device = plan, int(rank), device
+        self.D_in, self.D_out, self.dtype = int(D_in), int(D_out), dtype
+        self.means = torch.zeros((max(1, plan.rows_local), D_in), dtype=dtype, device=device)
+        self.variances = torch.ones((max(1, plan.rows_local), D_in), dtype=dtype, device=device)
+        self.result = torch.zeros((max(1, plan.rows_total), D_out), dtype=dtype, device=device)
+        self.meta = []
+        for b in range(plan.n_buckets):
+            ids = plan.members[b][self.rank]
+            lens = plan.lengths[ids]
+            self.meta.append({
+                "n_utt": len(ids), "max_T": int(lens.max(initial=0)),
+                "utt_off": torch.from_numpy(np.ascontiguousarray(plan.local_start[ids])).to(device),
+                "out_off": torch.from_numpy(np.ascontiguousarray(plan.row_start[ids])).to(device),
+                "utt_len": torch.from_numpy(lens.astype(np.int32)).to(device),
+            })
+
+    def load(self, means, variances):
+        """Copy this rank's utterances out of full host arrays (contiguous row slices, no fancy indexing)."""
+        import torch
+
+        plan = self.plan
+        off = np.concatenate([[0], np.cumsum(plan.lengths)])
+        var1d = np.asarray(variances).ndim == 1
+        if var1d:
+            self.variances = torch.from_numpy(np.ascontiguousarray(variances)).to(device=self.device, dtype=self.dtype)
+        for b in range(plan.n_buckets):
+            for u in plan.members[b][self.rank]:
+                a, e, l0 = int(off[u]), int(off[u + 1]), int(plan.local_start[u])
+                self.means[l0:l0 + e - a].copy_(torch.from_numpy(means[a:e]), non_blocking=True)
+                if not var1d:
+                    self.variances[l0:l0 + e - a].copy_(torch.from_numpy(variances[a:e]), non_blocking=True)
+        return self
+
+
+class ShardedResult(object):
+    """Gathered trajectories in shard order: utterance ``u`` is ``flat[row_start[u] : row_start[u] + lengths[u]]``."""
+
+    def __init__(self, flat, plan, timings=None):
+        self.flat, self.plan, self.timings = flat, plan, timings
+        self.row_start, self.lengths = plan.row_start, plan.lengths
+
+    def utterance(self, u):
+        a = int(self.row_start[u])
+        return self.flat[a:a + int(self.lengths[u])]
+
+    def to_utterance_order(self):
+        """``(sum_T, D_out)`` in the caller's utterance order (device segment copy; CPU tensors: slices)."""
+        import torch
+
+        lens = self.lengths
+        dst = np.concatenate([[0], np.cumsum(lens)])[:-1].astype(np.int64)
+        out = torch.empty((int(lens.sum()), self.flat.shape[1]), dtype=self.flat.dtype, device=self.flat.device)
+        if not self.flat.is_cuda:
+            for u in range(len(lens)):
+                out[int(dst[u]):int(dst[u]) + int(lens[u])] = self.utterance(u)
+            return out
+        from . import _device as dev
+        from . import _lib
+        dv = self.flat.device
+        src_t = torch.from_numpy(np.ascontiguousarray(self.row_start)).to(dv)
+        dst_t = torch.from_numpy(dst).to(dv)
+        len_t = torch.from_numpy(lens.astype(np.int32)).to(dv)
+        step = 65535
+        for s0 in range(0, len(lens), step):
+            n = min(step, len(lens) - s0)
+            _lib.check(_lib.lib.nnk_segment_copy(
+                self.flat.data_ptr(), out.data_ptr(), self.flat.element_size(), self.flat.shape[1], self.flat.shape[1],
+                out.shape[1], src_t[s0:].data_ptr(), dst_t[s0:].data_ptr(), len_t[s0:].data_ptr(), n,
+                int(lens[s0:s0 + n].max(initial=0)), dev.current_stream_ptr(dv)), "nnk_segment_copy")
+        return out
+
+
+def _solve_bucket(batch, b, windows_c, chains, n_chain, status):
+    """Enqueue the MLPG solve of bucket ``b`` on the current stream, trajectories written into the
+    rank's slot of ``batch.result`` (the single-GPU CUDA path; no collective)."""
+    from . import _device as dev
+
+    m = batch.meta[b]
+    if m["n_utt"] == 0 or m["max_T"] == 0:
+        return
+    var1d = batch.variances.dim() == 1
+    dev.run_mlpg("fwd", means=batch.means, variances=batch.variances, rhs=None, out=batch.result,
+                 offsets=m["utt_off"], lengths=m["utt_len"], order=None, chains=chains, n_chain=n_chain,
+                 max_T=m["max_T"], windows_c=windows_c, in_ld=batch.D_in, var_ld=0 if var1d else batch.D_in, go_ld=0,
+                 out_ld=batch.D_out, dtype_code=dev.torch_dtype_code(batch.dtype), go_f64=0, n_utt=m["n_utt"],
+                 device=batch.device, check=False, out_offsets=m["out_off"], status=status)
+
+
+def _gather_bucket(result, plan, b, rank, group):
+    """All-gather of bucket ``b`` (in place: every rank's block already sits in its slot)."""
+    import torch.distributed as dist
+
+    cap, g0, world = plan.cap[b], plan.goff[b], plan.world
+    if cap == 0:
+        return None
+    region = result[g0:g0 + world * cap]
+    mine = result[g0 + rank * cap:g0 + (rank + 1) * cap]
+    if dist.get_backend(group) == "nccl":
+        return dist.all_gather_into_tensor(region.view(-1), mine.view(-1), group=group, async_op=True)
+    parts = [region[r * cap:(r + 1) * cap] for r in range(world)]
+    tmp = [p.clone() for p in parts]
+    dist.all_gather(tmp, mine.clone(), group=group)
+    for p, t in zip(parts, tmp):
+        p.copy_(t)
+    return None
+
+
+def solve_sharded(batch, windows, layout, group=None, comm_stream=None, status=None):
+    """One pass over a resident :class:`ShardedBatch`: per bucket, solve then all-gather, the gather of
+    bucket ``b`` overlapping the solve of bucket ``b + 1``.  Returns the event that marks the end of
+    the pass on the current stream (after it, ``batch.result`` holds every rank's trajectories)."""
     import torch
     import torch.distributed as dist
 
-    world = dist.get_world_size(group)
-    cap = int(max(counts)) if len(counts) else 0
-    D = local.shape[1]
-    padded = torch.zeros((max(cap, 1), D), dtype=local.dtype, device=local.device)
-    padded[: local.shape[0]] = local
-    out = torch.empty((world, max(cap, 1), D), dtype=local.dtype, device=local.device)
-    if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(out.view(-1), padded.view(-1), group=group)
-    else:
-        parts = [torch.empty_like(padded) for _ in range(world)]
-        dist.all_gather(parts, padded, group=group)
-        out = torch.stack(parts)
-    return [out[r, : int(counts[r])] for r in range(world)]
+    from . import _device as dev
+    from . import _lib
+
+    plan, rank = batch.plan, batch.rank
+    is_cuda = batch.result.is_cuda
+    wc = _lib.make_windows(windows)
+    chains = dev.chains_on_device(layout.chains, batch.device) if is_cuda else None
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    assert world == plan.world
+    if not is_cuda or world == 1:
+        for b in range(plan.n_buckets):
+            _solve_bucket(batch, b, wc, chains, layout.n_chain, status)
+            if world > 1:
+                _gather_bucket(batch.result, plan, b, rank, group)
+        return None
+    cur = torch.cuda.current_stream(batch.device)
+    if comm_stream is None:
+        comm_stream = _comm_stream(batch.device)
+    works = []
+    for b in range(plan.n_buckets):
+        _solve_bucket(batch, b, wc, chains, layout.n_chain, status)
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(done)
+            works.append(_gather_bucket(batch.result, plan, b, rank, group))
+    for w in works:  # join: the current stream waits for every gather
+        if w is not None:
+            w.wait()
+    cur.wait_stream(comm_stream)
+    return None
 
 
-def mlpg_batch_sharded(means, variances, windows, lengths, layout=None, group=None, solve_fn=None, device=None):
-    """MLPG over a flat (sum_T, D) batch sharded by utterance over the ranks of ``group``.
+_comm_streams = {}
 
-    Every rank passes the SAME full inputs (NumPy) and gets the full ``(sum_T, D_out)`` result.
-    ``solve_fn(means_local, variances_local, windows, lengths_local, layout)`` defaults to the
-    single-GPU CUDA path (:func:`nnmnkwii_b200.paramgen.mlpg_batch` on device tensors).
+
+def _comm_stream(device):
+    import torch
+    key = str(device)
+    if key not in _comm_streams:
+        _comm_streams[key] = torch.cuda.Stream(device=device)
+    return _comm_streams[key]
+
+
+def mlpg_batch_sharded(means, variances, windows, lengths, layout=None, group=None, device=None, n_buckets=4,
+                       utterance_order=True):
+    """MLPG over a flat ``(sum_T, D)`` batch sharded by utterance over the ranks of ``group``.
+
+    Every rank passes the SAME full host inputs (NumPy) and keeps only its own utterances on its GPU;
+    every rank gets the full result: a ``(sum_T, D_out)`` tensor in utterance order
+    (``utterance_order=True``) or the :class:`ShardedResult` in shard order.  For a batch that is
+    already resident build a :class:`ShardedBatch` once and call :func:`solve_sharded` per pass.
     """
     import torch
     import torch.distributed as dist
@@ -66,25 +272,27 @@ def mlpg_batch_sharded(means, variances, windows, lengths, layout=None, group=No
     lengths = np.asarray(lengths, dtype=np.int64)
     if layout is None:
         layout = G.StreamLayout.single(means.shape[1], len(windows))
-    parts = partition(lengths, world)
-    mine = parts[rank]
-    rows = _flat_slice(lengths, mine)
-    var1d = np.asarray(variances).ndim == 1
-    m_loc = np.ascontiguousarray(means[rows])
-    v_loc = variances if var1d else np.ascontiguousarray(variances[rows])
-    if solve_fn is None:
-        if device is None:
-            device = torch.device("cuda", torch.cuda.current_device())
+    plan = ShardPlan(lengths, world, n_buckets)
+    if device is None:
+        device = _default_device()
+    dtype = torch.float32 if means.dtype == np.float32 and np.asarray(variances).dtype == np.float32 else torch.float64
+    np_dt = np.float32 if dtype == torch.float32 else np.float64
+    batch = ShardedBatch(plan, rank, device, layout.D_in, layout.D_out, dtype)
+    batch.load(np.ascontiguousarray(means, dtype=np_dt), np.ascontiguousarray(variances, dtype=np_dt))
+    status = torch.zeros(1, dtype=torch.int64, device=device) if batch.result.is_cuda else None
+    solve_sharded(batch, windows, layout, group, status=status)
+    if status is not None:
+        from . import _device as dev
+        dev.raise_if_failed(status)
+    res = ShardedResult(batch.result, plan)
+    return res.to_utterance_order() if utterance_order else res
 
-        def solve_fn(m, v, w, lens, lay):
-            return G.mlpg_batch(torch.from_numpy(m).to(device), torch.from_numpy(np.asarray(v)).to(device), w,
-                                lengths=lens, layout=lay)
-    y_loc = solve_fn(m_loc, v_loc, windows, lengths[mine], layout)
-    if not type(y_loc).__module__.startswith("torch"):
-        y_loc = torch.from_numpy(np.ascontiguousarray(y_loc))
-    counts = [int(lengths[p].sum()) for p in parts]
-    gathered = all_gather_rows(y_loc, counts, group)  # the ONE collective
-    out = torch.empty((int(lengths.sum()), layout.D_out), dtype=y_loc.dtype, device=y_loc.device)
-    for r in range(world):
-        out[torch.from_numpy(_flat_slice(lengths, parts[r])).to(out.device)] = gathered[r]
-    return out
+
+def _default_device():
+    import torch
+    from . import _device as dev
+    dev.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+_ = ctypes

@@ -90,6 +90,11 @@ def test_aligner_matches_reference_semantics():
             assert not Xa[n, len(oi):].any() and not Ya[n, len(oj):].any()
         # aligned distance < unaligned distance (test_preprocessing.py:464-501)
         assert np.linalg.norm(Xa - Ya) < np.linalg.norm(X - Y2)
+    # a user-written callable that computes the default cost (the reference's own default is such a
+    # lambda, alignment.py:35) takes the same kernel path as the sentinel default
+    Xd, Yd = DTWAligner(dist=lambda a, b: np.linalg.norm(a - b)).transform((X, Y2))
+    X0, Y0 = DTWAligner().transform((X, Y2))
+    assert np.array_equal(Xd, X0) and np.array_equal(Yd, Y0)
     with pytest.raises(NotImplementedError):
         DTWAligner(dist=lambda a, b: float(np.abs(a - b).sum())).transform((X, Y))
     with pytest.raises(AssertionError):  # alignment.py:42
@@ -137,7 +142,7 @@ def test_cfg4_size_properties():
             for v in c:
                 acc += v
             assert abs(acc - d[n]) <= 1e-9 * abs(d[n])
-        for n in (0, 7, 31):
+        for n in range(N):  # every pair against the C oracle
             d0, oi, oj, c0 = oracle.fastdtw(xs[n], ys[n], radius=radius, kind="melcd")
             assert np.array_equal(pi[n, :L[n]], oi) and np.array_equal(pj[n, :L[n]], oj)
             assert d[n] == d0 and cells[n] == c0

@@ -37,13 +37,47 @@ def _oracle_solve(m, v, w, lens, lay):
     return out
 
 
+def _oracle_bucket(windows):
+    """Stand-in for the per-rank CUDA solve (there is no GPU here): the oracle, writing each utterance
+    of the bucket into the rank's slot of the gather buffer exactly where the kernel would."""
+    def solve(batch, b, windows_c, chains, n_chain, status):
+        meta = batch.meta[b]
+        for k in range(meta["n_utt"]):
+            a, o, n = int(meta["utt_off"][k]), int(meta["out_off"][k]), int(meta["utt_len"][k])
+            y = oracle.mlpg(batch.means[a:a + n].numpy(), batch.variances[a:a + n].numpy(), windows)
+            batch.result[o:o + n] = torch.from_numpy(y)
+    return solve
+
+
+def test_plan_layout_is_complete_and_tight():
+    from nnmnkwii_b200.sharding import ShardPlan
+    rng = np.random.default_rng(0)
+    lens = rng.integers(200, 2001, size=8192)  # BASELINE.json configs[4]
+    for world in (1, 2, 4, 8):
+        plan = ShardPlan(lens, world, n_buckets=4)
+        seen = np.sort(np.concatenate([m for mem in plan.members for m in mem]))
+        assert np.array_equal(seen, np.arange(len(lens)))
+        # every utterance has its own rows inside its (bucket, rank) slot; slots do not overlap
+        ends = plan.row_start + lens
+        order = np.argsort(plan.row_start)
+        assert (plan.row_start[order][1:] >= ends[order][:-1]).all()
+        assert ends.max() <= plan.rows_total
+        # dead rows: at most one utterance per bucket and rank
+        assert plan.rows_total - lens.sum() <= plan.n_buckets * world * lens.max()
+        loads = np.array([plan.frames_of_rank(r) for r in range(world)])
+        assert loads.max() / loads.mean() < 1.002
+
+
 def _worker(rank, world, port, lens, m, v, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from nnmnkwii_b200.sharding import mlpg_batch_sharded
-    y = mlpg_batch_sharded(m, v, windows_set()[2], lens, solve_fn=_oracle_solve)
-    ret[rank] = y.numpy()
+    from nnmnkwii_b200 import sharding
+    w = windows_set()[2]
+    sharding._solve_bucket = _oracle_bucket(w)
+    y = sharding.mlpg_batch_sharded(m, v, w, lens, device=torch.device("cpu"), n_buckets=3)
+    res = sharding.mlpg_batch_sharded(m, v, w, lens, device=torch.device("cpu"), n_buckets=2, utterance_order=False)
+    ret[rank] = (y.numpy(), np.concatenate([res.utterance(u).numpy() for u in range(len(lens))]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,5 +96,6 @@ def test_two_rank_gloo_matches_single_process():
     mp.spawn(_worker, args=(2, port, lens, m, v, ret), nprocs=2, join=True)
     from nnmnkwii_b200 import paramgen as G
     ref = _oracle_solve(m, v, windows_set()[2], lens, G.StreamLayout.single(6, 3))
-    assert np.array_equal(ret[0], ref) and np.array_equal(ret[1], ref)
-    _ = (pytest, torch)
+    for r in (0, 1):
+        assert np.array_equal(ret[r][0], ref) and np.array_equal(ret[r][1], ref)
+    _ = pytest

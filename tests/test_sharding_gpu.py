@@ -44,3 +44,27 @@ def test_two_gpu_sharded_matches_single_gpu():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, lens, m, v, ret), nprocs=2, join=True)
     assert np.array_equal(ret[0], ref) and np.array_equal(ret[1], ref)
+
+
+def test_launch_follows_the_tensor_device_not_the_current_device():
+    """a tensor on cuda:1 while cuda:0 is current must run on cuda:1 (C ABI DeviceGuard)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from nnmnkwii_b200 import paramgen as G
+    from nnmnkwii_b200.metrics import melcd
+    rng = np.random.default_rng(6)
+    m = rng.random((50, 9), dtype=np.float32)
+    v = rng.random((50, 9), dtype=np.float32) + 0.1
+    torch.cuda.set_device(0)
+    ref = G.mlpg(torch.from_numpy(m).to("cuda:0"), torch.from_numpy(v).to("cuda:0"), windows_set()[2]).cpu().numpy()
+    y1 = G.mlpg(torch.from_numpy(m).to("cuda:1"), torch.from_numpy(v).to("cuda:1"), windows_set()[2])
+    assert y1.device.index == 1 and torch.cuda.current_device() == 0
+    assert np.array_equal(y1.cpu().numpy(), ref)
+    side = torch.cuda.Stream(device=1)
+    with torch.cuda.stream(side):  # a non-default stream of the other device
+        y2 = G.mlpg(torch.from_numpy(m).to("cuda:1"), torch.from_numpy(v).to("cuda:1"), windows_set()[2])
+    side.synchronize()
+    assert np.array_equal(y2.cpu().numpy(), ref)
+    a = torch.from_numpy(rng.random((4, 30, 5), dtype=np.float32))
+    b = torch.from_numpy(rng.random((4, 30, 5), dtype=np.float32))
+    assert abs(melcd(a.to("cuda:1"), b.to("cuda:1")) - melcd(a.to("cuda:0"), b.to("cuda:0"))) < 1e-12
