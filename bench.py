@@ -15,8 +15,13 @@ dimension of every utterance) over one batch of synthetic input.  Prints ONE JSO
               stream paramgen.mlpg as in its gallery notebooks) on this box's host cores
   --impl reference : times that CPU path only (rank 0), same metric/config/unit.
 
-Multi-GPU (torchrun, one rank per GPU): every rank solves its own 256-utterance slice (weak scaling,
-no data-path collective); one NCCL all_gather of the trajectories at the end, inside the timed region.
+Multi-GPU (torchrun, one rank per GPU, --gpus N > 1): BASELINE.json configs[4] -- the 8192-utterance
+ragged batch (T ~ U{200..2000}, 9.0e6 frames, D=187) STRONG-scaled over the ranks through
+nnmnkwii_b200.sharding (ShardPlan -> pre-sharded device buffers -> per bucket: solve, then in-place NCCL
+all-gather on a side stream while the next bucket solves).  One step = one full pass: every solve AND
+every all-gather, every step (nothing is amortised over --steps).  The line reports kernel ms, exposed
+all-gather ms and their sum.  The N=1 line carries `scale_workload`: the same 8192-utterance pass on
+one GPU, the denominator for the scaling efficiency of the N>1 lines.
 """
 import argparse
 import json
@@ -37,6 +42,8 @@ T_LO, T_HI = 540, 660
 D_IN, D_OUT = 187, 63
 ALGO_BYTES_PER_FRAME = 1744  # 186 cols mean + 186 cols variance in, 62 out, vuv copy 4+4 (f32)
 WINDOWS = [(0, 0, np.array([1.0])), (1, 1, np.array([-0.5, 0.0, 0.5])), (1, 1, np.array([1.0, -2.0, 1.0]))]
+# ncu --set full summaries of the dominant kernel on configs[1] (newest round first): roofline.traffic is parsed from them
+DOMINANT_PROFILES = ["r02_mlpg_dominant_cfg2*_ncu.txt", "r01_mlpg_v11_as_3a_l2pf_ncu.txt"]
 METRIC = "mlpg_frames_per_sec"
 UNIT = "frames/s"
 
@@ -60,13 +67,53 @@ def config(n_gpus):
     }
 
 
+# ---- configs[4]: 8192 utterances, mixed T, strong scaling ---------------------------------------------
+CFG5_UTT, CFG5_T_LO, CFG5_T_HI, CFG5_BUCKETS = 8192, 200, 2000, 4
+
+
+def cfg5_lengths():
+    return np.random.default_rng(4242).integers(CFG5_T_LO, CFG5_T_HI + 1, size=CFG5_UTT).astype(np.int64)
+
+
+def cfg5_utterance(u, T, device=None):
+    """Synthetic (T, 187) means / variances of utterance u: the same numbers on whichever rank makes them."""
+    import torch
+    g = torch.Generator(device=device if device is not None else "cpu").manual_seed(777000 + int(u))
+    m = torch.rand((int(T), D_IN), generator=g, device=device, dtype=torch.float32)
+    v = torch.rand((int(T), D_IN), generator=g, device=device, dtype=torch.float32) + 0.1
+    return m, v
+
+
+def config_cfg5(n_gpus):
+    return {
+        "workload": "configs[4]: %d-utterance paramgen.mlpg batch, T~U{%d..%d} (9.0e6 frames), D=187 Merlin layout, 3 windows, "
+                    "per-frame diagonal variances, float32 I/O, STRONG-scaled over %d GPU(s): ShardPlan (%d buckets, "
+                    "longest-first greedy per bucket), inputs pre-sharded in HBM, per bucket solve -> in-place NCCL "
+                    "all_gather_into_tensor overlapped with the next bucket; every rank ends with all trajectories"
+                    % (CFG5_UTT, CFG5_T_LO, CFG5_T_HI, n_gpus, CFG5_BUCKETS),
+        "utterances": CFG5_UTT, "static_dims": 62, "windows": 3, "buckets": CFG5_BUCKETS,
+        "sharding": "utterance-sharded, %d rank(s), %d bucketed all-gathers per pass (the path's only collective)"
+                    % (n_gpus, CFG5_BUCKETS),
+        "cache": "per-rank inputs (>= 1.7 GB) and factor scratch exceed the 126 MB L2; no explicit flush",
+    }
+
+
 # ---------------------------------------------------------------------------------------------------
 # CPU reference arm
 # ---------------------------------------------------------------------------------------------------
-def _ref_worker_init():
+def make_cfg5_sample(n_sample=256):
+    """Bounded CPU-arm sample of configs[4]: the first `n_sample` utterances of the 8192 (mixed T)."""
+    lens = cfg5_lengths()[:n_sample]
+    rng = np.random.default_rng(99)
+    n = int(lens.sum())
+    return lens, rng.random((n, D_IN), dtype=np.float32), rng.random((n, D_IN), dtype=np.float32) + np.float32(0.1)
+
+
+def _ref_worker_init(workload="cfg2"):
     os.environ["OMP_NUM_THREADS"] = "1"
     global _BATCH
-    lens, m, v = make_batch(0)  # workers own the data: no pickling of 230 MB through pipes per step
+    # workers own the data: no pickling of 230 MB through pipes per step
+    lens, m, v = make_cfg5_sample() if workload == "cfg5" else make_batch(0)
     _BATCH = (np.concatenate([[0], np.cumsum(lens)]), m, v)
     import warnings
     warnings.simplefilter("ignore")
@@ -106,7 +153,7 @@ def usable_cores():
     return n
 
 
-def cpu_reference(lens, means, variances, n_sample, repeats, cores=None):
+def cpu_reference(lens, means, variances, n_sample, repeats, cores=None, workload="cfg2"):
     """frames/s of the reference CPU path on `n_sample` utterances of the workload.  The reference is
     single-threaded; it is given one process per core, and because oversubscribed or throttled hosts
     make "all cores" slower than fewer, a few pool sizes are tried and the fastest is reported."""
@@ -126,7 +173,7 @@ def cpu_reference(lens, means, variances, n_sample, repeats, cores=None):
     best = None
     tried = {}
     for size in sizes:
-        with ctx.Pool(size, initializer=_ref_worker_init) as pool:
+        with ctx.Pool(size, initializer=_ref_worker_init, initargs=(workload,)) as pool:
             pool.map(_ref_one, items[: max(size, 8)])  # warm-up (imports, page-in)
             times = []
             for _ in range(repeats):
@@ -147,12 +194,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    lens, means, variances = make_batch(0)
+    # N > 1: our arm runs configs[4] (8192 ragged utterances); the CPU arm times a 256-utterance sample of it
+    workload = "cfg5" if args.gpus > 1 else "cfg2"
+    lens, means, variances = make_cfg5_sample() if workload == "cfg5" else make_batch(0)
     steps, warm = max(1, args.steps), max(0, args.warmup)
     # each step = one bounded sample of the workload (whole batch is ~1.5 CPU-seconds on one core)
-    n_sample = N_UTT
-    probe, _, _ = cpu_reference(lens, means, variances, n_sample, 3)          # pick the best pool size (best of 3 each)
-    base, times, frames = cpu_reference(lens, means, variances, n_sample, steps + warm, probe["cores"])
+    n_sample = len(lens)
+    probe, _, _ = cpu_reference(lens, means, variances, n_sample, 3, workload=workload)  # best pool size (best of 3 each)
+    base, times, frames = cpu_reference(lens, means, variances, n_sample, steps + warm, probe["cores"], workload=workload)
     base["sample"] = probe["sample"].rsplit(", best of", 1)[0] + ", %d timed steps" % steps
     timed = times[warm:] if len(times) > warm else times
     total = sum(timed)
@@ -160,8 +209,10 @@ def run_reference(args):
     base["value"] = val
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
-        "warmup": warm, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args.gpus),
+        "warmup": warm, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
+        "scaling": "strong" if workload == "cfg5" else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_cfg5(args.gpus) if workload == "cfg5" else config(args.gpus),
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -228,6 +279,205 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profile_traffic(patterns):
+    """DRAM bytes per launch of the dominant kernel, parsed from the newest committed ncu summary under
+    profiles/ whose name matches `pattern` (dram__bytes_read.sum + dram__bytes_write.sum of one
+    `ncu --set full` capture), so that the number in the JSON line and the profile cannot drift."""
+    import glob
+    import re
+    files = []
+    for pattern in patterns:  # first pattern with a match wins (newest round first)
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
+        if files:
+            break
+    for f in reversed(files):
+        txt = open(f).read()
+        got = {}
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(r"^%s\s+(\S+)\s+([0-9.eE+-]+)\s*$" % re.escape(key), txt, re.M)
+            if m:
+                unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(1))
+                if unit:
+                    got[key] = float(m.group(2)) * unit
+        if len(got) == 2:
+            return sum(got.values()), "profiles/%s (ncu --set full: dram__bytes_read.sum %.1f MB + dram__bytes_write.sum " \
+                "%.1f MB per launch)" % (os.path.basename(f), got["dram__bytes_read.sum"] / 1e6, got["dram__bytes_write.sum"] / 1e6)
+    return None, "no ncu --set full summary matching profiles/%s" % (patterns,)
+
+
+class Cfg5Pass(object):
+    """configs[4] resident on this rank in ShardPlan layout + one timed pass over it."""
+
+    def __init__(self, rank, world, device):
+        import torch
+        from nnmnkwii_b200 import paramgen as G
+        from nnmnkwii_b200 import sharding
+        self.rank, self.world, self.device = rank, world, device
+        self.lens = cfg5_lengths()
+        self.layout = G.merlin_layout()
+        self.plan = sharding.ShardPlan(self.lens, world, CFG5_BUCKETS)
+        self.batch = sharding.ShardedBatch(self.plan, rank, device, D_IN, D_OUT, torch.float32)
+        for b in range(self.plan.n_buckets):  # inputs are generated straight into the rank's HBM slice
+            for u in self.plan.members[b][rank]:
+                m, v = cfg5_utterance(u, self.lens[u], device)
+                l0 = int(self.plan.local_start[u])
+                self.batch.means[l0:l0 + m.shape[0]] = m
+                self.batch.variances[l0:l0 + m.shape[0]] = v
+        self.status = torch.zeros(1, dtype=torch.int64, device=device)
+        self.frames_local = self.plan.frames_of_rank(rank)
+        self.frames_total = int(self.lens.sum())
+
+    def run(self, group=None):
+        from nnmnkwii_b200 import sharding
+        sharding.solve_sharded(self.batch, WINDOWS, self.layout, group, status=self.status)
+
+    def solve_only(self):
+        from nnmnkwii_b200 import _device as dev
+        from nnmnkwii_b200 import _lib
+        from nnmnkwii_b200 import sharding
+        wc = _lib.make_windows(WINDOWS)
+        chains = dev.chains_on_device(self.layout.chains, self.device)
+        for b in range(self.plan.n_buckets):
+            sharding._solve_bucket(self.batch, b, wc, chains, self.layout.n_chain, self.status)
+
+    def gather_only(self, group=None):
+        from nnmnkwii_b200 import sharding
+        works = [sharding._gather_bucket(self.batch.result, self.plan, b, self.rank, group) for b in range(self.plan.n_buckets)]
+        for w in works:
+            if w is not None:
+                w.wait()
+
+    def parity(self, utts):
+        """max relative error vs the oracle of the gathered trajectories of a few utterances (any owner)."""
+        import oracle
+        worst = 0.0
+        for u in utts:
+            m, v = cfg5_utterance(u, self.lens[u], self.device)
+            m, v = m.cpu().numpy(), v.cpu().numpy()
+            a = int(self.plan.row_start[u])
+            got = self.batch.result[a:a + int(self.lens[u])].cpu().numpy()
+            ref = oracle.mlpg(m[:, :180], v[:, :180], WINDOWS)
+            worst = max(worst, float(np.abs(got[:, :60] - ref).max() / np.abs(ref).max()))
+            assert np.array_equal(got[:, 61], m[:, 183])  # the copied vuv column
+        return worst
+
+
+def _timed(fn, steps, warmup, barrier):
+    import torch
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_sharded(args, rank, world, local):
+    """--gpus N > 1: configs[4] strong-scaled (see module docstring)."""
+    import torch
+    import torch.distributed as dist
+    from nnmnkwii_b200 import _device as dev
+    from nnmnkwii_b200 import _lib
+    from nnmnkwii_b200 import paramgen as G
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    job = Cfg5Pass(rank, world, device)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    warm = max(3, args.warmup)
+    sampler = ClockSampler(local)
+    for _ in range(warm):
+        job.run()
+    barrier()
+    dev.raise_if_failed(job.status)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    n0 = _lib.launch_count()
+    pass_ms = reduce_max(_timed(job.run, args.steps, 0, barrier))          # the metric: solve + gather, every step
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms = reduce_max(_timed(job.solve_only, max(3, args.steps // 2), 1, barrier))   # the solves alone (slowest rank)
+    gather_ms = reduce_max(_timed(job.gather_only, max(3, args.steps // 2), 1, barrier))  # the 4 all-gathers alone
+    value = job.frames_total / (pass_ms * 1e-3)
+    parity = None
+    if rank == 0:
+        owners = {int(job.plan.owner[u]): u for u in range(CFG5_UTT - 1, -1, -1)}  # one utterance of every rank
+        parity = job.parity(sorted(owners.values())[: min(world, 4)])
+
+    # e2e at N GPUs: every rank pushes ITS shard through the public host-buffer API (pinned NumPy in,
+    # NumPy out: H2D + solve + D2H every step); the trajectories land in host memory sharded the same way
+    mine = np.concatenate([job.plan.members[b][rank] for b in range(job.plan.n_buckets)])
+    lens_loc = job.lens[mine]
+    rows = int(lens_loc.sum())
+    hm = torch.empty((rows, D_IN), dtype=torch.float32).pin_memory()
+    hv = torch.empty((rows, D_IN), dtype=torch.float32).pin_memory()
+    o = 0
+    for u in mine:
+        a = int(job.plan.local_start[u])
+        n = int(job.lens[u])
+        hm[o:o + n].copy_(job.batch.means[a:a + n])
+        hv[o:o + n].copy_(job.batch.variances[a:a + n])
+        o += n
+    hy = torch.empty((rows, D_OUT), dtype=torch.float32).pin_memory().numpy()
+    hm, hv = hm.numpy(), hv.numpy()
+    G.mlpg_batch(hm, hv, WINDOWS, lengths=lens_loc, layout=job.layout, out=hy)
+    barrier()
+    e2e_steps = 3
+    n1 = _lib.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        G.mlpg_batch(hm, hv, WINDOWS, lengths=lens_loc, layout=job.layout, out=hy)
+    torch.cuda.synchronize()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    launches += _lib.launch_count() - n1
+    e2e_val = job.frames_total * e2e_steps / e2e_s
+    h2d = reduce_max(float(hm.nbytes + hv.nbytes))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    achieved = ALGO_BYTES_PER_FRAME * job.frames_local / (kernel_ms * 1e-3) / 1e9
+    out_bytes = job.plan.rows_total * D_OUT * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": pass_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_cfg5(world),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(rows * D_OUT * 4),
+                "steps": e2e_steps, "api": "per rank: nnmnkwii_b200.paramgen.mlpg_batch(numpy pinned, its shard of configs[4]) -> "
+                "nnk_mlpg_batch_host; bytes are per rank (largest shard); no gather: results stay sharded in host memory"},
+        "gpu_launches": int(launches),
+        "kernel_ms": kernel_ms, "allgather_ms": gather_ms, "allgather_exposed_ms": max(0.0, pass_ms - kernel_ms),
+        "kernel_plus_allgather_ms": kernel_ms + gather_ms,
+        "allgather": {"bytes_received_per_rank": int(out_bytes * (world - 1) / world), "buckets": job.plan.n_buckets,
+                      "alone_gbs_per_rank": out_bytes * (world - 1) / world / (gather_ms * 1e-3) / 1e9,
+                      "note": "every rank must RECEIVE (N-1)/N of the 2.27 GB result per pass: at N=8 that is 1.98 GB over one "
+                              "NVLink port (<= 900 GB/s/dir) >= 2.2 ms against ~1.05 ms of solve -- the pass is NVLink-receive "
+                              "bound, which no overlap can hide; the solves alone scale as kernel_ms shows"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "mlpg_fwd_as_kernel (per rank, %d bucket launches)" % job.plan.n_buckets,
+                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * job.frames_local},
+        "cpu_baseline": None, "clocks": clocks, "parity_max_rel_err_vs_oracle": parity,
+        "frames_per_step_per_gpu": job.frames_local, "frames_per_step": job.frames_total,
+    }
+    print(json.dumps(line))
+
+
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
@@ -239,6 +489,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    if world > 1:
+        return run_sharded(args, rank, world, local)
     lens, means, variances = make_batch(rank)
 
     # CPU baseline first (rank 0, before CUDA is touched in this process; spawn-based pool)
@@ -248,8 +500,6 @@ def run_ours(args):
 
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
 
     from nnmnkwii_b200 import _device as dev
     from nnmnkwii_b200 import _lib
@@ -275,9 +525,6 @@ def run_ours(args):
                             in_ld=D_IN, var_ld=D_IN, go_ld=0, out_ld=D_OUT, dtype_code=_lib.NNK_F32, go_f64=0,
                             n_utt=N_UTT, device=device, check=False)
 
-    gathered = torch.empty((world, T_HI * N_UTT, D_OUT), dtype=torch.float32, device=device) if world > 1 else None
-    pad_out = torch.zeros((T_HI * N_UTT, D_OUT), dtype=torch.float32, device=device) if world > 1 else None
-
     for _ in range(max(3, args.warmup)):
         status = step()
     torch.cuda.synchronize()
@@ -289,8 +536,6 @@ def run_ours(args):
         time.sleep(0.2)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -302,27 +547,12 @@ def run_ours(args):
         kev[i][0].record()
         step()
         kev[i][1].record()
-    ag_ms = 0.0
-    if world > 1:  # the one collective: all_gather of the trajectories at the end of the job
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        pad_out[:n_rows].copy_(d_out)
-        dist.all_gather_into_tensor(gathered.view(-1), pad_out.view(-1))
-        a1.record()
     ev1.record()
     barrier()
     launches = _lib.launch_count() - n0
     total_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        ag_ms = a0.elapsed_time(a1)
     kernel_ms = [a.elapsed_time(b) for a, b in kev]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
-    frames_t = torch.tensor([float(n_rows)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(frames_t, op=dist.ReduceOp.SUM)
-    total_ms = float(t.item())
-    frames_all = float(frames_t.item())
+    frames_all = float(n_rows)
     value = frames_all * args.steps / (total_ms * 1e-3)
 
     # parity spot check of what was just timed (utterance 0, mgc stream) against the oracle
@@ -350,26 +580,24 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     launches += _lib.launch_count() - n1
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = frames_all * e2e_steps / float(te.item())
+    e2e_val = frames_all * e2e_steps / e2e_s
     if rank == 0:
         assert np.array_equal(y[: int(off_np[1])], d_out[: int(off_np[1])].cpu().numpy()), "e2e and device paths disagree"
 
-    extras = None
-    if rank == 0 and world == 1 and not args.no_extras:
+    clocks = sampler.stop()  # the clocks of the timed region (+ the e2e arm), not of the side measurements
+    extras = dtw = scale = None
+    if not args.no_extras:
         try:
             extras = bench_extras(device)
+            dtw = extras.pop("dtw", None)
         except Exception as e:  # the headline line must survive a failure of the side measurements
             extras = {"error": repr(e)}
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return
+        try:
+            scale = bench_cfg5_single(device, max(3, min(10, args.steps)))
+        except Exception as e:
+            scale = {"error": repr(e)}
     peak, peak_src = measured_peak()
+    traffic, traffic_src = profile_traffic(DOMINANT_PROFILES)
     k_ms = statistics.mean(kernel_ms)
     achieved = ALGO_BYTES_PER_FRAME * n_rows / (k_ms * 1e-3) / 1e9
     line = {
@@ -381,17 +609,17 @@ def run_ours(args):
                 "api": "nnmnkwii_b200.paramgen.mlpg_batch(numpy pinned) -> nnk_mlpg_batch_host"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 705.4e6, "traffic_source": "profiles/r01_mlpg_v11_as_3a_l2pf_ncu.txt (ncu --set full: "
-                     "dram__bytes_read.sum 438.6 MB + dram__bytes_write.sum 266.8 MB per launch; the excess over the "
-                     "algorithmic bytes is the float64 factor scratch round trip)", "peak_source": peak_src, "kernel": ("mlpg_kernel<float,3,1,1,FWD> (register prefetch)" if os.environ.get("NNK_MLPG_DIRECT") == "1" else
+                     "traffic": traffic, "traffic_source": traffic_src + "; the excess over the algorithmic bytes is the "
+                     "float64 factor scratch round trip", "peak_source": peak_src, "kernel": ("mlpg_kernel<float,3,1,1,FWD> (register prefetch)" if os.environ.get("NNK_MLPG_DIRECT") == "1" else
                                 "mlpg_fwd_tma_kernel<float,3,1,1,STD> (single warp)" if os.environ.get("NNK_MLPG_SINGLE") == "1" else
                                 "mlpg_fwd_as_kernel<float,3,1,1,STD> (3 assembler warps + 1 solver warp per 32 chains)"),
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * n_rows},
         "cpu_baseline": cpu_base,
         "clocks": clocks,
-        "allgather_ms": ag_ms,
         "parity_max_rel_err_vs_oracle": parity,
         "frames_per_step_per_gpu": n_rows,
+        "dtw": dtw,
+        "scale_workload": scale,
         "other_kernels": extras,
     }
     print(json.dumps(line))
@@ -445,15 +673,71 @@ def _device_ms(fn, reps):
         return e0.elapsed_time(e1) / reps, "eager"
 
 
+def _dtw_cpu_one(args):
+    import oracle
+    x, y, radius = args
+    return oracle.fastdtw(x, y, radius=radius, kind="melcd")[3]
+
+
+def dtw_cpu_baseline(X, Y, n_c=64, n_py=16):
+    """CPU numbers beside the DTW kernels: OUR restatement, not the fastdtw package
+    (absent, unpinned: setup.py:139).  (i) the C oracle -- exact O(Tx*Ty) DP and FastDTW(radius=1), float64,
+    same 3-way min / tie order -- one process per host core on `n_c` pairs; (ii) the faithful pure-Python
+    FastDTW with a per-cell Python callback (what a user of the reference experiences) on `n_py` pairs, 1 core."""
+    import multiprocessing as mp
+    import oracle
+    from oracle import fastdtw_py
+    lens = lambda A, n: int(np.flatnonzero(np.abs(A[n]).sum(1) >= 1e-7)[-1] + 1)
+    pairs = [(X[n, :lens(X, n)], Y[n, :lens(Y, n)]) for n in range(len(X))]
+    n_c, n_py = min(n_c, len(pairs)), min(n_py, len(pairs))
+    cores = min(usable_cores(), n_c)
+    out = {"kind": "port", "label": "restated oracle, not fastdtw", "cores": cores,
+           "sample": "C oracle: all %d pairs FastDTW(radius=1), %d pairs exact DP (%d processes); per-cell-callback Python "
+                     "FastDTW: %d pairs (1 core)" % (len(pairs), n_c, cores, n_py)}
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_dtw_cpu_one, [(p[0][:50], p[1][:50], 1) for p in pairs[:cores]])  # warm-up: imports, library load
+        for name, radius in (("fastdtw_radius1", 1), ("exact", -1)):
+            t0 = time.perf_counter()
+            sub = pairs if radius > 0 else pairs[:n_c]
+            cells = sum(pool.map(_dtw_cpu_one, [(p[0], p[1], radius) for p in sub], chunksize=1))
+            out[name + "_c_oracle"] = {"value": cells / (time.perf_counter() - t0), "unit": "cell-updates/s", "cores": cores}
+    t0 = time.perf_counter()
+    cells = 0
+    for x, y in pairs[:n_py]:
+        cells += fastdtw_py.fastdtw(x, y, radius=1, dist=lambda a, b: oracle.LOGDB_CONST * np.sqrt(((a - b) ** 2).sum()),
+                                    return_cells=True)[2]
+    out["fastdtw_radius1_python_callback"] = {"value": cells / (time.perf_counter() - t0), "unit": "cell-updates/s", "cores": 1}
+    return out
+
+
+def bench_cfg5_single(device, steps):
+    """configs[4] on ONE GPU, measured like the N>1 arm (same plan, buckets, kernels; no collective): the
+    denominator of the scaling efficiency of the --gpus N lines."""
+    import torch
+    job = Cfg5Pass(0, 1, device)
+    ms = _timed(job.solve_only, steps, 2, torch.cuda.synchronize)
+    from nnmnkwii_b200 import _device as dev
+    dev.raise_if_failed(job.status)
+    worst = job.parity([0, CFG5_UTT - 1])
+    peak, _ = measured_peak()
+    gbs = ALGO_BYTES_PER_FRAME * job.frames_total / (ms * 1e-3) / 1e9
+    return {"workload": config_cfg5(1)["workload"], "value": job.frames_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "steps": steps, "frames_per_step": job.frames_total, "hbm_gbs_algorithmic": gbs, "roofline_frac": gbs / peak,
+            "parity_max_rel_err_vs_oracle": worst}
+
+
 def bench_extras(device, reps=5):
     import torch
     from nnmnkwii_b200 import autograd as AF
     from nnmnkwii_b200 import paramgen as G
     from nnmnkwii_b200.preprocessing import alignment as A
     out = {}
-    # --- DTW, configs[3]: 512 pairs, melcd cost ------------------------------------------------------
+    # --- DTW, configs[3]: 512 pairs, melcd cost; cell updates/s next to the CPU restatement ------------------
     X, Y = make_dtw_pairs(512)
     Xd, Yd = torch.from_numpy(X).to(device), torch.from_numpy(Y).to(device)
+    dtw = {"workload": "configs[3]: 512 pairs, T~U{700..900}, 25-dim, melcd local cost; trim + DTW per batch (no gather)",
+           "unit": "cell-updates/s", "parity": "paths, cell counts and distance bit-identical to the restated oracle "
+           "(tests/test_dtw_gpu.py); the real fastdtw package is absent: parity unpinned"}
     for name, radius in (("fastdtw_radius1", 1), ("exact", -1)):
         res = A._align_batch(Xd, Yd, 1, radius)
         torch.cuda.synchronize()
@@ -465,8 +749,9 @@ def bench_extras(device, reps=5):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         cells = int(res.cells.sum().item())
-        out["dtw_" + name] = {"cell_updates_per_sec": cells / (ms * 1e-3), "cells_per_batch": cells, "pairs": 512,
-                              "ms_per_batch": ms, "cost": "melcd", "includes": "trim + DTW (no gather)"}
+        dtw[name] = {"value": cells / (ms * 1e-3), "cells_per_batch": cells, "pairs": 512, "ms_per_batch": ms}
+    dtw["cpu_baseline"] = dtw_cpu_baseline(X, Y)
+    out["dtw"] = dtw
     # --- UnitVarianceMLPG fwd + loss.backward(), configs[2] ---------------------------------------------
     T, sd, B = 1000, 60, 64
     R = torch.from_numpy(G.unit_variance_mlpg_matrix(WINDOWS, T)).to(device)
