@@ -160,6 +160,16 @@ int nnk_uv_apply_toeplitz(const void* table, const float* taps, const void* x, v
                           int32_t sd, int32_t nw, int32_t K, int32_t t_lo, int32_t t_hi, int32_t backward,
                           int32_t reshaped, void* stream);
 
+/* Factored float32 variant: in the shift-invariant rows every window block of R is one long filter h0
+ * (a row of P^-1) convolved with a short window stencil, h_w = h0 * c_w; the host recovers c_w from R
+ * (HOST pointers: h0 2K+1 floats, c nw x (2*KC+1) floats) and the sweep costs (2K+1) + ~7 multiply-adds
+ * per output instead of nw*(2K+1) (replaces the same two torch.matmul calls, mlpg.py:138 / :158).
+ * Packs two static dims per thread for any static_dim (odd ones, e.g. the reference's perf grid
+ * static_dim = 59, perf/autograd_mlpg_perf.py:110-120, use predicated 4-byte accesses).              */
+int nnk_uv_apply_factored(const void* table, const float* h0, const float* c, const void* x, void* y, int32_t B,
+                          int32_t T, int32_t sd, int32_t nw, int32_t K, int32_t KC, int32_t t_lo, int32_t t_hi,
+                          int32_t backward, int32_t reshaped, void* stream);
+
 /* ---- DTW alignment (preprocessing/alignment.py:9-190) ------------------------------------------
  * Batched replacement of `dist, path = fastdtw(x, y, radius=self.radius, dist=self.dist)`
  * (alignment.py:50, :138; third-party slaypni/fastdtw, unpinned in setup.py:139 -- see DESIGN.md

@@ -93,7 +93,7 @@ CHAIN_DTYPE = np.dtype([("in_col", np.int32), ("win_stride", np.int32), ("out_co
 EXPORTS = [
     "nnk_abi_version", "nnk_last_error", "nnk_launch_count", "nnk_status_decode",
     "nnk_mlpg_fwd", "nnk_mlpg_grad", "nnk_mlpg_solve", "nnk_mlpg_workspace_bytes", "nnk_mlpg_host", "nnk_mlpg_batch_host",
-    "nnk_uv_band_profile", "nnk_uv_band_extract", "nnk_uv_apply", "nnk_uv_apply_toeplitz",
+    "nnk_uv_band_profile", "nnk_uv_band_extract", "nnk_uv_apply", "nnk_uv_apply_toeplitz", "nnk_uv_apply_factored",
     "nnk_dtw_align", "nnk_dtw_workspace_bytes", "nnk_gather_rows", "nnk_trim_lengths", "nnk_delta_features",
     "nnk_metric_workspace_bytes", "nnk_frame_metric", "nnk_f0_metric", "nnk_segment_copy",
 ]
@@ -138,6 +138,8 @@ def _load():
     L.nnk_uv_apply.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.nnk_uv_apply_toeplitz.restype = ctypes.c_int
     L.nnk_uv_apply_toeplitz.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.nnk_uv_apply_factored.restype = ctypes.c_int
+    L.nnk_uv_apply_factored.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.nnk_dtw_align.restype = ctypes.c_int
     L.nnk_dtw_align.argtypes = [ctypes.POINTER(NnkDtwArgs), vp]
     L.nnk_dtw_workspace_bytes.restype = ctypes.c_size_t

@@ -9,20 +9,28 @@ from . import _device as dev
 from . import _lib
 from ._lib import lib
 
-# relative magnitude (w.r.t. max |R|) below which off-band entries of R are dropped.  R is float32
-# (resolution 6e-8); everything dropped sums to well below that.  K = T - 1 reproduces R exactly.
-BAND_REL_TOL = 2.0 ** -32
+# relative magnitude (w.r.t. max |R|) below which off-band entries of R are dropped.  A float32 R has
+# resolution 6e-8 (2^-24): everything dropped sums to well below that.  A float64 R is only cut where
+# its entries are below ITS resolution.  K = T - 1 reproduces R exactly (an arbitrary dense R simply
+# gets K = T - 1 and the per-row table kernels: nothing is ever silently banded).
+BAND_REL_TOL = {"float32": 2.0 ** -32, "float64": 2.0 ** -60}
 
 _band_cache = {}
 
 
-# rows whose band differs from the middle row by less than this (relative to max |R|) share its filter
-TOEPLITZ_REL_TOL = 2.0 ** -22
+# rows whose band differs from the middle row by less than this (relative to max |R|) share its filter.
+# R's own float32 rounding makes two copies of the same filter differ by up to 2^-24 max|R| per entry, so
+# 2^-23 is the tightest test that still recognises the shift-invariant rows; per output the substitution
+# error is then bounded by (2K+1) nw 2^-23 max|R| max|x| (5e-5 at K = 23) and is ~ sqrt of that count in
+# practice, the level of the float32 rounding of R itself.  float32 R only.
+TOEPLITZ_REL_TOL = 2.0 ** -23
 TOEPLITZ_MIN_ROWS = 64
+# h_w = h_0 * c_w fit (factored sweep): accepted when the residual is below the same resolution
+FACTOR_REL_TOL = 2.0 ** -23
 
 
 class Band(object):
-    __slots__ = ("Rb", "RbT", "K", "T", "nw", "dtype", "toep", "toepT")
+    __slots__ = ("Rb", "RbT", "K", "T", "nw", "dtype", "toep", "toepT", "fact", "factT")
 
 
 def _toeplitz_interval(table, peak):
@@ -40,6 +48,35 @@ def _toeplitz_interval(table, peak):
     while hi < T and ok[hi]:
         hi += 1
     return lo, hi, np.ascontiguousarray(tab[mid], dtype=np.float32)
+
+
+def _factor_taps(taps, K, peak):
+    """Short stencils c_w (nw, 2*KC+1) with  taps[w] = taps[0] * c_w  (h_w[j] = sum_k c_w[k] h_0[j - k + KC]),
+    KC in (1, 2), by least squares on the band row; None if the residual exceeds FACTOR_REL_TOL * peak
+    (e.g. an R that is not an MLPG matrix).  Host side, once per R."""
+    import numpy as np
+    h = np.asarray(taps, dtype=np.float64)
+    nw, W = h.shape
+    if nw < 2 or nw > 3 or K > 32:
+        return None
+    for KC in (1, 2):
+        A = np.zeros((W, 2 * KC + 1))
+        for k in range(2 * KC + 1):
+            for j in range(W):
+                i = j - k + KC
+                if 0 <= i < W:
+                    A[j, k] = h[0, i]
+        c = np.zeros((nw, 2 * KC + 1))
+        good = True
+        for w in range(nw):
+            sol = np.linalg.lstsq(A, h[w], rcond=None)[0]
+            if np.abs(A @ sol - h[w]).max() > peak * FACTOR_REL_TOL:
+                good = False
+                break
+            c[w] = sol
+        if good:
+            return KC, np.ascontiguousarray(h[0], dtype=np.float32), np.ascontiguousarray(c, dtype=np.float32)
+    return None
 
 
 def band_of(R, device):
@@ -61,7 +98,7 @@ def band_of(R, device):
     _lib.check(lib.nnk_uv_band_profile(Rd.data_ptr(), code, T, nw, profile.data_ptr(), stream), "nnk_uv_band_profile")
     prof = profile.cpu()
     peak = float(prof.max())
-    above = torch.nonzero(prof > peak * BAND_REL_TOL)
+    above = torch.nonzero(prof > peak * BAND_REL_TOL["float64" if Rd.dtype == torch.float64 else "float32"])
     K = int(above.max()) if above.numel() else 0
     b = Band()
     b.K, b.T, b.nw, b.dtype = K, T, nw, Rd.dtype
@@ -69,14 +106,16 @@ def band_of(R, device):
     b.RbT = torch.empty((T, nw, 2 * K + 1), dtype=Rd.dtype, device=device)
     _lib.check(lib.nnk_uv_band_extract(Rd.data_ptr(), code, T, nw, K, b.Rb.data_ptr(), b.RbT.data_ptr(), stream),
                "nnk_uv_band_extract")
-    b.toep = b.toepT = None
+    b.toep = b.toepT = b.fact = b.factT = None
     if Rd.dtype == torch.float32 and nw <= 3 and K <= 64 and T >= TOEPLITZ_MIN_ROWS:
         lo, hi, taps = _toeplitz_interval(b.Rb, peak)
         if hi - lo >= TOEPLITZ_MIN_ROWS:
             b.toep = (lo, hi, taps)
+            b.fact = _factor_taps(taps, K, peak)
         lo, hi, taps = _toeplitz_interval(b.RbT, peak)
         if hi - lo >= TOEPLITZ_MIN_ROWS:
             b.toepT = (lo, hi, taps)
+            b.factT = _factor_taps(taps, K, peak)
     if len(_band_cache) > 16:
         _band_cache.clear()
     try:
@@ -100,7 +139,13 @@ def apply_forward(band, means3, reshaped):
             means3 = means3[..., : nw * sd]
     x = means3.to(band.dtype).contiguous()
     y = torch.empty((B, T, sd), dtype=band.dtype, device=x.device)
-    if band.toep is not None:
+    if band.toep is not None and band.fact is not None:
+        lo, hi, _ = band.toep
+        kc, h0, c = band.fact
+        _lib.check(lib.nnk_uv_apply_factored(band.Rb.data_ptr(), h0.ctypes.data, c.ctypes.data, x.data_ptr(), y.data_ptr(),
+                                             B, T, sd, nw, band.K, kc, lo, hi, 0, int(reshaped),
+                                             dev.current_stream_ptr(x.device)), "nnk_uv_apply_factored")
+    elif band.toep is not None:
         lo, hi, taps = band.toep
         _lib.check(lib.nnk_uv_apply_toeplitz(band.Rb.data_ptr(), taps.ctypes.data, x.data_ptr(), y.data_ptr(), B, T, sd, nw,
                                              band.K, lo, hi, 0, int(reshaped), dev.current_stream_ptr(x.device)),
@@ -121,7 +166,13 @@ def apply_backward(band, grad_output3, reshaped, D):
         gx = torch.empty((B, nw * T, sd), dtype=band.dtype, device=g.device)
     else:
         gx = torch.empty((B, T, nw * sd), dtype=band.dtype, device=g.device)
-    if band.toepT is not None:
+    if band.toepT is not None and band.factT is not None:
+        lo, hi, _ = band.toepT
+        kc, h0, c = band.factT
+        _lib.check(lib.nnk_uv_apply_factored(band.RbT.data_ptr(), h0.ctypes.data, c.ctypes.data, g.data_ptr(), gx.data_ptr(),
+                                             B, T, sd, nw, band.K, kc, lo, hi, 1, int(reshaped),
+                                             dev.current_stream_ptr(g.device)), "nnk_uv_apply_factored")
+    elif band.toepT is not None:
         lo, hi, taps = band.toepT
         _lib.check(lib.nnk_uv_apply_toeplitz(band.RbT.data_ptr(), taps.ctypes.data, g.data_ptr(), gx.data_ptr(), B, T, sd, nw,
                                              band.K, lo, hi, 1, int(reshaped), dev.current_stream_ptr(g.device)),

@@ -342,6 +342,235 @@ static int uv_apply(const void* tab, const void* x, void* y, int B, int Tn, int 
                              : uv_apply_bb<T, 4>(tab, x, y, B, Tn, sd, nw, K, backward, reshaped, skip_lo, skip_hi, st);
 }
 
+// ---- factored Toeplitz path ------------------------------------------------------------------------------
+// R = P^-1 [Wt_0^T .. Wt_{nw-1}^T]: away from the ends every window block of R is the SAME long filter
+// h_0 (a row of P^-1, 2K+1 taps) convolved with a short window stencil c_w (2KC+1 taps, KC <= 2):
+//     h_w = h_0 * c_w.
+// The host recovers c_w from R alone (least squares on the band rows, residual checked against the
+// float32 resolution of R; nnk_uv_apply_toeplitz stays the path when the fit fails), and the sweeps become
+//     forward :  b[s] = sum_w sum_k c_w[k] mu_w[s + k - KC]         (short stencils, ~7 FMAs)
+//                y[t] = sum_j h_0[j] b[t + j - K]                    (ONE long filter)
+//     backward:  a[r] = sum_j hT_0[j] o[r + j - K]                   (ONE long filter)
+//                g_w[s] = sum_k cT_w[k] a[s + k - KC]                (short stencils)
+// i.e. (2K+1) + ~7 multiply-adds per output instead of nw * (2K+1): 54 instead of 147 at T = 1000.
+// One CTA = (batch item, 32 dim PAIRS, time tile).  The intermediate (b or a) of the tile plus its halo
+// lives in shared memory [position][lane] as float2; a thread owns two adjacent static dims, all
+// multiply-adds are packed FFMA2 whose filter operand is a (h, h) pair in a uniform register
+// (constant bank) -- the kernel needs 32-40 registers.  Odd static_dim: the pair (d, d+1) straddles
+// the row end for the last lane only; loads and stores of the second element are predicated
+// (VEC = false: two 4-byte accesses, the multiply-adds stay packed).
+template <int KK, int KC, int NWT>
+struct UvFactTaps {
+  float2 h0[2 * KK + 1];          // (h, h) pairs of the long filter
+  float2 c[NWT][2 * KC + 1];      // (c, c) pairs of the short stencils
+};
+
+template <bool VEC>
+__device__ __forceinline__ float2 uv_ld2(const float* p, bool ok0, bool ok1) {
+  if (VEC) return ok0 ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f);
+  float2 v;
+  v.x = ok0 ? __ldg(p) : 0.f;
+  v.y = ok1 ? __ldg(p + 1) : 0.f;
+  return v;
+}
+template <bool VEC>
+__device__ __forceinline__ void uv_st2(float* p, float2 v, bool ok0, bool ok1) {
+  if (VEC) {
+    if (ok0) *reinterpret_cast<float2*>(p) = v;
+  } else {
+    if (ok0) p[0] = v.x;
+    if (ok1) p[1] = v.y;
+  }
+}
+
+constexpr int UVF_TTU = 8;  // outputs of the long filter per register block
+
+// forward: tile of TC output frames; stage 1 fills sb[p] = b[t0 - KK + p], p < TC + 2 KK
+template <int KK, int KC, int NWT, int TC, bool VEC>
+__global__ void __launch_bounds__(128) uv_fact_fwd_kernel(const __grid_constant__ UvFactTaps<KK, KC, NWT> taps,
+                                                          const float* __restrict__ x, float* __restrict__ y, int Tn, int sd,
+                                                          int nw, int t_lo, int t_hi, int reshaped) {
+  constexpr int NP = TC + 2 * KK;      // intermediate positions of the tile
+  constexpr int PW = NP / 4;           // ... per warp
+  constexpr int CH = 4;                // stage-1 positions per register block
+  static_assert(NP % 4 == 0 && PW % CH == 0 && TC % (4 * UVF_TTU) == 0, "tile geometry");
+  extern __shared__ __align__(16) float2 sb[];  // [NP][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = 2 * (blockIdx.y * 32 + lane);
+  const bool ok0 = d < sd, ok1 = d + 1 < sd;
+  const int b = blockIdx.z;
+  const int t0 = t_lo + blockIdx.x * TC;
+  const int64_t nwsd = (int64_t)nw * sd;
+  const float* xb = x + (int64_t)b * Tn * nwsd + d;
+  // ---- stage 1: short stencils -> b ----
+#pragma unroll 1
+  for (int blk = 0; blk < PW / CH; ++blk) {
+    const int p0 = warp * PW + blk * CH;
+    const int s0 = t0 - KK + p0;  // first position of the block
+    float2 acc[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < NWT; ++w) {
+      if (w < nw) {
+#pragma unroll
+        for (int r = 0; r < CH + 2 * KC; ++r) {  // frame s0 - KC + r feeds position i with tap k = r - i
+          const int s = s0 - KC + r;
+          const bool in = (s >= 0 && s < Tn);
+          const int sc = in ? s : 0;
+          const int64_t off = reshaped ? ((int64_t)w * Tn + sc) * sd : (int64_t)sc * nwsd + (int64_t)w * sd;
+          const float2 v = uv_ld2<VEC>(xb + off, ok0 && in, ok1 && in);
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int k = r - i;
+            if (k >= 0 && k <= 2 * KC) acc[i] = __ffma2_rn(taps.c[w][k], v, acc[i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) sb[(p0 + i) * 32 + lane] = acc[i];
+  }
+  __syncthreads();
+  // ---- stage 2: the long filter ----
+  constexpr int OW = TC / 4;  // outputs per warp
+#pragma unroll 1
+  for (int blk = 0; blk < OW / UVF_TTU; ++blk) {
+    const int o0 = warp * OW + blk * UVF_TTU;  // first output of the block, relative to t0
+    if (t0 + o0 >= t_hi) break;
+    float2 acc[UVF_TTU];
+#pragma unroll
+    for (int i = 0; i < UVF_TTU; ++i) acc[i] = make_float2(0.f, 0.f);
+    const float2* src = sb + o0 * 32 + lane;  // b[t0 + o0 - KK + r] = sb[o0 + r]
+#pragma unroll
+    for (int r = 0; r < UVF_TTU + 2 * KK; ++r) {
+      const float2 v = src[r * 32];
+#pragma unroll
+      for (int i = 0; i < UVF_TTU; ++i) {
+        const int j = r - i;
+        if (j >= 0 && j <= 2 * KK) acc[i] = __ffma2_rn(taps.h0[j], v, acc[i]);
+      }
+    }
+    float* yo = y + ((int64_t)b * Tn + t0 + o0) * sd + d;
+#pragma unroll
+    for (int i = 0; i < UVF_TTU; ++i)
+      if (t0 + o0 + i < t_hi) uv_st2<VEC>(yo + (int64_t)i * sd, acc[i], ok0, ok1);
+  }
+}
+
+// backward: tile of TC = 64 - 2 KC rows; stage 1 fills sa[p] = a[s0 - KC + p], p < 64 (the long filter,
+// inputs from global / L1); stage 2 applies the short stencils and writes the nw gradient streams
+template <int KK, int KC, int NWT, bool VEC>
+__global__ void __launch_bounds__(128) uv_fact_bwd_kernel(const __grid_constant__ UvFactTaps<KK, KC, NWT> taps,
+                                                          const float* __restrict__ go, float* __restrict__ gx, int Tn, int sd,
+                                                          int nw, int t_lo, int t_hi, int reshaped) {
+  constexpr int NP = 64, TC = NP - 2 * KC, PW = NP / 4;
+  __shared__ __align__(16) float2 sa[NP * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = 2 * (blockIdx.y * 32 + lane);
+  const bool ok0 = d < sd, ok1 = d + 1 < sd;
+  const int b = blockIdx.z;
+  const int s0 = t_lo + blockIdx.x * TC;
+  const float* gb = go + (int64_t)b * Tn * sd + d;
+  // ---- stage 1: a[r], r = s0 - KC + p ----
+#pragma unroll 1
+  for (int blk = 0; blk < PW / UVF_TTU; ++blk) {
+    const int p0 = warp * PW + blk * UVF_TTU;
+    const int r0 = s0 - KC + p0 - KK;  // first input frame of the block
+    float2 acc[UVF_TTU];
+#pragma unroll
+    for (int i = 0; i < UVF_TTU; ++i) acc[i] = make_float2(0.f, 0.f);
+    const bool interior = (r0 >= 0) && (r0 + UVF_TTU + 2 * KK <= Tn);
+    if (interior) {
+#pragma unroll
+      for (int r = 0; r < UVF_TTU + 2 * KK; ++r) {
+        const float2 v = uv_ld2<VEC>(gb + (int64_t)(r0 + r) * sd, ok0, ok1);
+#pragma unroll
+        for (int i = 0; i < UVF_TTU; ++i) {
+          const int j = r - i;
+          if (j >= 0 && j <= 2 * KK) acc[i] = __ffma2_rn(taps.h0[j], v, acc[i]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < UVF_TTU + 2 * KK; ++r) {
+        const int t = r0 + r;
+        const bool in = (t >= 0 && t < Tn);
+        const float2 v = uv_ld2<VEC>(gb + (int64_t)(in ? t : 0) * sd, ok0 && in, ok1 && in);
+#pragma unroll
+        for (int i = 0; i < UVF_TTU; ++i) {
+          const int j = r - i;
+          if (j >= 0 && j <= 2 * KK) acc[i] = __ffma2_rn(taps.h0[j], v, acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < UVF_TTU; ++i) sa[(p0 + i) * 32 + lane] = acc[i];
+  }
+  __syncthreads();
+  // ---- stage 2: g_w[s] = sum_k c_w[k] a[s + k - KC], s = s0 + q: a[s + k - KC] = sa[q + k] ----
+  const int64_t nwsd = (int64_t)nw * sd;
+  float* ob = gx + (int64_t)b * Tn * nwsd + d;
+  for (int q = warp; q < TC; q += 4) {
+    const int s = s0 + q;
+    if (s >= t_hi) break;
+    float2 v[2 * KC + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * KC; ++k) v[k] = sa[(q + k) * 32 + lane];
+#pragma unroll
+    for (int w = 0; w < NWT; ++w) {
+      if (w < nw) {
+        float2 g = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k <= 2 * KC; ++k) g = __ffma2_rn(taps.c[w][k], v[k], g);
+        const int64_t off = reshaped ? ((int64_t)w * Tn + s) * sd : (int64_t)s * nwsd + (int64_t)w * sd;
+        uv_st2<VEC>(ob + off, g, ok0, ok1);
+      }
+    }
+  }
+}
+
+template <int KK, int KC>
+static int uv_fact_launch(const float* h0, const float* c, const float* x, float* y, int B, int Tn, int sd, int nw, int K,
+                          int kc, int t_lo, int t_hi, int backward, int reshaped, cudaStream_t st) {
+  constexpr int NWT = 3;
+  UvFactTaps<KK, KC, NWT> taps;
+  for (int j = 0; j <= 2 * KK; ++j) {  // pad the long filter to the instantiated half-width
+    const int jj = j - (KK - K);
+    const float v = (jj >= 0 && jj <= 2 * K) ? h0[jj] : 0.f;
+    taps.h0[j] = make_float2(v, v);
+  }
+  for (int w = 0; w < NWT; ++w)
+    for (int k = 0; k <= 2 * KC; ++k) {
+      const int kk = k - (KC - kc);
+      const float v = (w < nw && kk >= 0 && kk <= 2 * kc) ? c[w * (2 * kc + 1) + kk] : 0.f;
+      taps.c[w][k] = make_float2(v, v);
+    }
+  const int rows = t_hi - t_lo;
+  const bool vec = (sd % 2 == 0) && (((uintptr_t)x | (uintptr_t)y) % 8 == 0);
+  const unsigned gy = (unsigned)(((sd + 1) / 2 + 31) / 32);
+  if (!backward) {
+    constexpr int TC = 64;
+    constexpr size_t smem = (size_t)(TC + 2 * KK) * 32 * sizeof(float2);
+    dim3 grid((unsigned)((rows + TC - 1) / TC), gy, (unsigned)B);
+    if (vec) {
+      NNK_CUDA_CHECK(cudaFuncSetAttribute(uv_fact_fwd_kernel<KK, KC, NWT, TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      uv_fact_fwd_kernel<KK, KC, NWT, TC, true><<<grid, 128, smem, st>>>(taps, x, y, Tn, sd, nw, t_lo, t_hi, reshaped);
+    } else {
+      NNK_CUDA_CHECK(cudaFuncSetAttribute(uv_fact_fwd_kernel<KK, KC, NWT, TC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      uv_fact_fwd_kernel<KK, KC, NWT, TC, false><<<grid, 128, smem, st>>>(taps, x, y, Tn, sd, nw, t_lo, t_hi, reshaped);
+    }
+  } else {
+    constexpr int TC = 64 - 2 * KC;
+    dim3 grid((unsigned)((rows + TC - 1) / TC), gy, (unsigned)B);
+    if (vec) uv_fact_bwd_kernel<KK, KC, NWT, true><<<grid, 128, 0, st>>>(taps, x, y, Tn, sd, nw, t_lo, t_hi, reshaped);
+    else uv_fact_bwd_kernel<KK, KC, NWT, false><<<grid, 128, 0, st>>>(taps, x, y, Tn, sd, nw, t_lo, t_hi, reshaped);
+  }
+  count_launch();
+  NNK_CUDA_CHECK(cudaGetLastError());
+  return NNK_OK;
+}
+
 }  // namespace nnk
 
 using namespace nnk;
@@ -419,4 +648,36 @@ extern "C" int nnk_uv_apply_toeplitz(const void* table, const float* taps, const
   }
 #undef NNK_TOEP
   return NNK_ERR_UNSUPPORTED;
+}
+
+// Factored variant of nnk_uv_apply_toeplitz (float32): rows [t_lo, t_hi) are computed as ONE long filter
+// `h0` (HOST, 2K+1 floats: the band row of the static-window block) combined with short per-window
+// stencils `c` (HOST, nw x (2*KC+1) floats) such that the band row of window w equals h0 * c[w]
+// (the host fits c from R and checks the residual); the remaining edge rows use the per-row table.
+// Supported: nw <= 3, K <= 32, KC <= 2 (otherwise NNK_ERR_UNSUPPORTED: call nnk_uv_apply_toeplitz).
+extern "C" int nnk_uv_apply_factored(const void* table, const float* h0, const float* c, const void* x, void* y, int32_t B,
+                                     int32_t T, int32_t sd, int32_t nw, int32_t K, int32_t KC, int32_t t_lo, int32_t t_hi,
+                                     int32_t backward, int32_t reshaped, void* stream) {
+  NNK_REQUIRE(table && h0 && c && x && y, NNK_ERR_ARG, "NULL pointer");
+  NNK_REQUIRE(B >= 0 && T > 0 && sd >= 0 && nw > 0 && K >= 0 && KC >= 0 && t_lo >= 0 && t_hi <= T && t_lo <= t_hi, NNK_ERR_ARG, "bad size");
+  if (B == 0 || sd == 0) return NNK_OK;
+  NNK_REQUIRE(nw <= 3 && K <= 32 && KC <= 2, NNK_ERR_UNSUPPORTED, "factored path supports nw <= 3, K <= 32, KC <= 2");
+  NNK_REQUIRE(B <= 65535 && (sd + 63) / 64 <= 65535, NNK_ERR_ARG, "batch or static_dim too large for one launch");
+  DeviceGuard guard(x);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = uv_apply<float>(table, x, y, B, T, sd, nw, K, backward, reshaped, t_lo, t_hi, st);  // edge rows
+  if (rc || t_hi == t_lo) return rc;
+  const float* xf = (const float*)x;
+  float* yf = (float*)y;
+#define NNK_FACT(KV, CV) return uv_fact_launch<KV, CV>(h0, c, xf, yf, B, T, sd, nw, K, KC, t_lo, t_hi, backward, reshaped, st)
+  if (KC <= 1) {
+    if (K <= 16) NNK_FACT(16, 1);
+    if (K <= 24) NNK_FACT(24, 1);
+    NNK_FACT(32, 1);
+  } else {
+    if (K <= 16) NNK_FACT(16, 2);
+    if (K <= 24) NNK_FACT(24, 2);
+    NNK_FACT(32, 2);
+  }
+#undef NNK_FACT
 }

@@ -203,3 +203,77 @@ def test_batched_mlpg_autograd_matches_per_utterance():
     off = np.concatenate([[0], np.cumsum(lens)])
     for b, n in enumerate(lens):
         assert torch.equal(yf[off[b]:off[b + 1]], yp[b, :n])
+
+
+@pytest.mark.parametrize("sd,T,reshaped,nwin", [(59, 500, False, 3), (24, 500, True, 3), (60, 333, False, 3), (5, 260, False, 2),
+                                                 (1, 200, True, 3)])
+def test_unit_variance_factored_sweeps_match_dense(sd, T, reshaped, nwin):
+    """The factored Toeplitz path (one long filter + short window stencils, packed dim pairs) on the
+    reference's own perf grid (static_dim 24 / 59, T 500: perf/autograd_mlpg_perf.py:110-120) and odd /
+    tiny static dims, both layouts, forward and backward, against the float64 dense product with the
+    SAME R."""
+    AF, G = _mods()
+    from nnmnkwii_b200 import _uvmlpg as uv
+    ws = windows_set()[2][:nwin]
+    R = torch.from_numpy(G.unit_variance_mlpg_matrix(ws, T)).cuda()
+    band = uv.band_of(R, R.device)
+    assert band.fact is not None and band.factT is not None, "factored path not selected"
+    assert band.fact[0] == 1 and np.allclose(band.fact[2][0], [0, 1, 0], atol=1e-6)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B = 3
+    mu = torch.randn(B, T, nwin * sd, device="cuda", generator=g)
+    x = mu.view(B, T, nwin, sd).transpose(1, 2).reshape(B, nwin * T, sd).contiguous() if reshaped else mu
+    x = x.requires_grad_(True)
+    y = AF.unit_variance_mlpg(R, x)
+    o = torch.randn(B, T, sd, device="cuda", generator=g)
+    (gx,) = torch.autograd.grad(y, x, o)
+    Rd = R.double()
+    for b in range(B):
+        xr = mu[b].double().view(T, nwin, sd).transpose(0, 1).reshape(nwin * T, sd)
+        yref = Rd @ xr
+        assert rel_err(y[b].detach().cpu().numpy(), yref.cpu().numpy()) < 2e-6
+        gref = Rd.t() @ o[b].double()  # (nw*T, sd)
+        if not reshaped:
+            gref = gref.view(nwin, T, sd).transpose(0, 1).reshape(T, nwin * sd)
+        assert rel_err(gx[b].cpu().numpy(), gref.cpu().numpy()) < 2e-6
+
+
+def test_unit_variance_arbitrary_dense_R_is_applied_exactly():
+    """an R that is NOT an MLPG matrix (dense random) is never silently banded: K = T - 1, the
+    per-row table kernels, result == torch.mm to float32 rounding; float64 R keeps float64 accuracy."""
+    AF, G = _mods()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    T, sd = 70, 5
+    for dt, tol in ((torch.float32, 2e-6), (torch.float64, 1e-13)):
+        R = torch.randn(T, 3 * T, device="cuda", generator=g, dtype=dt)
+        x = torch.randn(2, 3 * T, sd, device="cuda", generator=g, dtype=dt).requires_grad_(True)
+        y = AF.unit_variance_mlpg(R, x)
+        ref = torch.matmul(R.double(), x.detach().double())
+        assert rel_err(y.detach().cpu().numpy(), ref.cpu().numpy()) < tol
+        o = torch.randn_like(y)
+        (gx,) = torch.autograd.grad(y, x, o)
+        gref = torch.matmul(R.double().t(), o.double())
+        assert rel_err(gx.cpu().numpy(), gref.cpu().numpy()) < tol
+
+
+def test_unit_variance_step_is_cuda_graph_capturable():
+    """after the one-off band extraction the forward + backward sweeps issue no host
+    synchronisation (no .item(), no upload): a whole step can be captured and replayed as a CUDA graph."""
+    AF, G = _mods()
+    ws = windows_set()[2]
+    T, sd, B = 300, 59, 4
+    R = torch.from_numpy(G.unit_variance_mlpg_matrix(ws, T)).cuda()
+    mu = torch.randn(B, T, 3 * sd, device="cuda").requires_grad_(True)
+    o = torch.randn(B, T, sd, device="cuda")
+    (g_eager,) = torch.autograd.grad(AF.unit_variance_mlpg(R, mu), mu, o)  # warm-up: builds + caches the band
+    y_eager = AF.unit_variance_mlpg(R, mu).detach().clone()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            y = AF.unit_variance_mlpg(R, mu)
+            (gx,) = torch.autograd.grad(y, mu, o)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y.detach(), y_eager) and torch.equal(gx, g_eager)
