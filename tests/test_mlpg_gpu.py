@@ -348,3 +348,55 @@ def test_mlpg_grad_batch_merlin_layout():
             want[a:b, 183] = go[a:b, 61]
             want[a:b, 184:187] = oracle.mlpg_grad(z[:, :3], vv(184, 187), ws, go[a:b, 62:63])
         assert rel_err(got, want) < 2e-6, global_var
+
+
+def test_ring_protocol_stress_many_launches_reused_scratch():
+    """the assembler/solver ring protocol under launch pressure -- hundreds of
+    back-to-back launches, odd lengths (tiles that end mid-ring, T smaller than one tile), narrow and
+    wide chain groups, scratch handed back and forth by the caching allocator, two streams at once.
+    Every launch must be bit-identical to the first run of the same inputs and match the oracle."""
+    import torch
+    G = _G()
+    ws = windows_set()[2]
+    rng = np.random.default_rng(77)
+    cases = []
+    for T, sd in ((1, 1), (3, 59), (5, 60), (13, 3), (31, 33), (97, 59), (100, 59), (255, 60), (300, 7), (641, 62)):
+        m = rng.random((T, 3 * sd), dtype=np.float32)
+        v = rng.random((T, 3 * sd), dtype=np.float32) + 0.1
+        mt, vt = torch.from_numpy(m).cuda(), torch.from_numpy(v).cuda()
+        first = G.mlpg(mt, vt, ws).clone()
+        assert rel_err(first.cpu().numpy(), oracle.mlpg(m, v, ws)) < TOL32
+        cases.append((mt, vt, first))
+    side = torch.cuda.Stream()
+    outs = []
+    for it in range(40):
+        for k, (mt, vt, first) in enumerate(cases):
+            if (it + k) % 3 == 0:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    outs.append((k, G.mlpg_batch(mt, vt, ws, lengths=[mt.shape[0]], check=False)))
+            else:
+                outs.append((k, G.mlpg_batch(mt, vt, ws, lengths=[mt.shape[0]], check="deferred")))
+        if it % 10 == 9:
+            torch.cuda.synchronize()
+            for k, y in outs:
+                assert torch.equal(y, cases[k][2]), "launch %d differs" % k
+            outs = []
+    from nnmnkwii_b200 import _device as dev
+    dev.poll_errors(block=True)
+
+
+def test_deferred_check_surfaces_not_positive_definite():
+    """check='deferred' never blocks, and the LinAlgError still arrives (at poll_errors / the next call)."""
+    import torch
+    from nnmnkwii_b200 import _device as dev
+    G = _G()
+    ws = windows_set()[2]
+    m = torch.rand(20, 9, device="cuda")
+    v = torch.rand(20, 9, device="cuda") + 0.1
+    v[7, 0] = -1.0  # a negative variance makes a pivot non-positive
+    dev.poll_errors(block=True)
+    G.mlpg_batch(m, v, ws, lengths=[20], check="deferred")
+    with pytest.raises(np.linalg.LinAlgError):
+        dev.poll_errors(block=True)
+    dev.poll_errors(block=True)  # the record is consumed
