@@ -722,6 +722,194 @@ __global__ void __launch_bounds__(256) dtw_dp_kernel(const DtwExactParams p) {
   }
 }
 
+// ---- exact DTW, fused (the production path for frames of 8..39 dims that fit shared memory) -----------------
+// One CTA per pair, one wavefront: the local cost of a cell is computed in registers at the moment the
+// recurrence needs it -- there is NO Tx x Ty cost matrix in HBM (the two-kernel path above wrote and
+// re-read 8 bytes per cell: 5 GB per configs[3] batch against 0.25 GB of algorithmic traffic).
+//   * all of Y (float64, conflict-free row stride) is staged ONCE in shared memory;
+//   * the rows of X are processed in strips of R = 512: thread r of a strip owns row i = strip*R + r and
+//     keeps its frame of X in registers (float64) for the whole strip;
+//   * step k of a strip relaxes the cells (r, j = k - r): cost from registers x shared-memory Y in
+//     numpy's pairwise order (bit-exact, no FMA contraction), predecessors from the thread's own
+//     register (left), from the neighbouring thread through three rolling shared-memory diagonals (up,
+//     diagonal), or -- for the first row of a strip -- from the last row of the previous strip kept in
+//     shared memory; one __syncthreads per step;
+//   * back-pointers are 2 bits per cell, packed by the owning thread into one 32-bit word per 16
+//     columns, row-major in an L2-resident scratch (40 KB.. 200 KB per pair instead of 1 byte per cell);
+//   * the back-track is a pointer chase: warp 0 loads a 32-row x 32-column window of back-pointer words
+//     with one coalesced round trip, walks it by shuffles, and reloads when the path leaves the window.
+constexpr int DTW_FR = 512;
+
+struct DtwFusedParams {
+  const void* X;
+  const void* Y;
+  int64_t x_pair_stride, y_pair_stride;
+  int x_ld, y_ld, D;
+  const int32_t* len_x;
+  const int32_t* len_y;
+  const int32_t* order;
+  int cost_kind;
+  int32_t* path_i;
+  int32_t* path_j;
+  int path_ld;
+  int32_t* path_len;
+  double* dist;
+  long long* cells;
+  int max_tx, max_ty;
+  uint32_t* bp;  // [pair slot][max_tx][wpr]
+  int wpr;       // back-pointer words per row = ceil(max_ty / 16)
+  double logdb;
+};
+
+template <typename T, int NB8>
+__global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedParams p) {
+  constexpr int R = DTW_FR;
+  extern __shared__ __align__(16) unsigned char smem_f[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = blockIdx.x;
+  const int pair = p.order ? p.order[slot] : slot;
+  const int Tx = p.len_x[pair], Ty = p.len_y[pair];
+  if (Tx <= 0 || Ty <= 0) {
+    if (tid == 0) { p.path_len[pair] = 0; p.dist[pair] = 0.0; if (p.cells) p.cells[pair] = 0; }
+    return;
+  }
+  const int D = p.D, DP = dtw_row_stride(D);
+  double* Ys = reinterpret_cast<double*>(smem_f);          // [max_ty][DP]
+  double* Dk = Ys + (size_t)p.max_ty * DP;                 // [3][R] rolling diagonals of the strip
+  double* Dl = Dk + 3 * R;                                 // [2][max_ty] last row of the previous / current strip
+  const T* X = reinterpret_cast<const T*>(p.X) + (int64_t)pair * p.x_pair_stride;
+  const T* Y = reinterpret_cast<const T*>(p.Y) + (int64_t)pair * p.y_pair_stride;
+  for (int e = tid; e < Ty * D; e += R) {
+    const int r = e / D, k = e - r * D;
+    Ys[(size_t)r * DP + k] = (double)Y[(int64_t)r * p.y_ld + k];
+  }
+  uint32_t* bp = p.bp + (size_t)slot * ((size_t)p.max_tx * p.wpr);
+  const int ntail = D - NB8 * 8;
+  const int nstrip = (Tx + R - 1) / R;
+  for (int s = 0; s < nstrip; ++s) {
+    const int i = s * R + tid;
+    const bool row_ok = i < Tx;
+    const int rows = min(R, Tx - s * R);
+    double xreg[NB8 * 8 + 8];
+#pragma unroll
+    for (int e = 0; e < NB8 * 8 + 8; ++e) xreg[e] = (row_ok && e < D) ? (double)X[(int64_t)i * p.x_ld + e] : 0.0;
+    const double* Dlp = Dl + (size_t)(s & 1) * p.max_ty;        // written by strip s - 1
+    double* Dlc = Dl + (size_t)((s + 1) & 1) * p.max_ty;        // written by this strip
+    double myD = 0.0;
+    uint32_t bpw = 0;
+    uint32_t* bprow = bp + (size_t)i * p.wpr;
+    __syncthreads();  // Ys staged (s == 0) / previous strip's last row complete
+    const int nsteps = rows + Ty - 1;
+    for (int k = 0; k < nsteps; ++k) {
+      const int j = k - tid;
+      if (row_ok && j >= 0 && j < Ty) {
+        const double* yr = Ys + (size_t)j * DP;
+        double r8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const double z = __dsub_rn(xreg[q], yr[q]); r8[q] = __dmul_rn(z, z); }
+#pragma unroll
+        for (int bk = 1; bk < NB8; ++bk) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const double z = __dsub_rn(xreg[bk * 8 + q], yr[bk * 8 + q]);
+            r8[q] = __dadd_rn(r8[q], __dmul_rn(z, z));
+          }
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r8[0], r8[1]), __dadd_rn(r8[2], r8[3])),
+                               __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
+#pragma unroll
+        for (int e = 0; e < 7; ++e)
+          if (e < ntail) { const double z = __dsub_rn(xreg[NB8 * 8 + e], yr[NB8 * 8 + e]); res = __dadd_rn(res, __dmul_rn(z, z)); }
+        const double rt = sqrt(res);
+        const double dt = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
+        // predecessors: D[i-1][j] (up), D[i][j-1] (left), D[i-1][j-1] (diagonal)
+        double dup, ddg;
+        if (tid > 0) {
+          dup = Dk[((k + 2) % 3) * R + tid - 1];
+          ddg = (j > 0) ? Dk[((k + 1) % 3) * R + tid - 1] : CUDART_INF;
+        } else if (s > 0) {
+          dup = Dlp[j];
+          ddg = (j > 0) ? Dlp[j - 1] : CUDART_INF;
+        } else {
+          dup = CUDART_INF;
+          ddg = (j == 0) ? 0.0 : CUDART_INF;
+        }
+        const double up = dup + dt;
+        const double left = ((j > 0) ? myD : CUDART_INF) + dt;
+        const double diag = ddg + dt;
+        double best = up;
+        uint32_t dir = 0;
+        if (left < best) { best = left; dir = 1; }
+        if (diag < best) { best = diag; dir = 2; }
+        myD = best;
+        Dk[(k % 3) * R + tid] = best;
+        if (tid == rows - 1) Dlc[j] = best;
+        bpw |= dir << (2 * (j & 15));
+        if ((j & 15) == 15 || j == Ty - 1) { bprow[j >> 4] = bpw; bpw = 0; }
+        if (i == Tx - 1 && j == Ty - 1) p.dist[pair] = best;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- back-track (warp 0) ----
+  __shared__ int s_n;
+  if (warp == 0) {
+    int i = Tx - 1, j = Ty - 1, n = 0;
+    bool ok = true;
+    int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
+    int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
+    while (ok && i >= 0 && j >= 0) {
+      const int bi = i, bw = j >> 4;
+      const int r = bi - lane;
+      const uint32_t w0 = (r >= 0) ? __ldcg(bp + (size_t)r * p.wpr + bw) : 0u;
+      const uint32_t w1 = (r >= 0 && bw > 0) ? __ldcg(bp + (size_t)r * p.wpr + bw - 1) : 0u;
+      while (i >= 0 && j >= 0 && bi - i < 32 && (j >> 4) >= bw - 1) {
+        if (n >= p.path_ld) { ok = false; break; }
+        if (lane == 0) { pi[n] = i; pj[n] = j; }
+        ++n;
+        const bool second = (j >> 4) != bw;
+        const uint32_t word = __shfl_sync(0xffffffffu, second ? w1 : w0, bi - i);
+        const uint32_t dir = (word >> (2 * (j & 15))) & 3u;
+        if (dir == 0) --i;
+        else if (dir == 1) --j;
+        else { --i; --j; }
+      }
+    }
+    if (lane == 0) s_n = ok ? n : -1;
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > 0) {
+    int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
+    int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
+    for (int a = tid; a < n / 2; a += R) {
+      const int b = n - 1 - a;
+      const int32_t ti = pi[a], tj = pj[a];
+      pi[a] = pi[b]; pj[a] = pj[b];
+      pi[b] = ti; pj[b] = tj;
+    }
+  }
+  if (tid == 0) {
+    p.path_len[pair] = n;
+    if (p.cells) p.cells[pair] = (long long)Tx * Ty;
+  }
+}
+
+static size_t dtw_fused_smem(int max_ty, int D) {
+  int dp = (D + 1) & ~1;
+  if (((dp >> 1) & 1) == 0) dp += 2;
+  return sizeof(double) * ((size_t)max_ty * dp + 3 * DTW_FR + 2 * (size_t)max_ty) + 16;
+}
+// the fused kernel serves frames of 8..39 dimensions whose Y series fits shared memory as float64
+static bool dtw_fused_ok(int max_ty, int D, size_t max_smem) {
+  return D >= 8 && D < 40 && dtw_fused_smem(max_ty, D) <= max_smem;
+}
+static bool dtw_force_two_pass() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NNK_DTW_TWO_PASS"); v = (e && e[0] == '1') ? 1 : 0; }  // A/B measurements only
+  return v == 1;
+}
+
 // pairs per chunk of the exact mode: 9 bytes per cell (float64 cost + back-pointer), <= ~2 GiB per chunk
 static int dtw_exact_chunk(int n_pairs, int max_tx, int max_ty) {
   const size_t per = (size_t)max_tx * (size_t)max_ty * 9;
@@ -807,9 +995,13 @@ using namespace nnk;
 
 extern "C" size_t nnk_dtw_workspace_bytes(int32_t n_pairs, int32_t max_tx, int32_t max_ty, int32_t D, int32_t radius) {
   const int mt = max_tx > max_ty ? max_tx : max_ty;
-  if (radius < 0) {  // exact: chunked float64 cost matrix + back-pointers, diagonal-major
+  if (radius < 0) {
+    // exact, two-pass fallback: chunked float64 cost matrix + back-pointers, diagonal-major;
+    // exact, fused: 2-bit back-pointers only, (max_ty / 16 + 1) words per row, every pair at once
     const size_t ch = (size_t)dtw_exact_chunk(n_pairs, max_tx, max_ty);
-    return ((ch * (size_t)max_tx * (size_t)max_ty * 9 + 255) / 256 * 256) + 256;
+    const size_t two_pass = ((ch * (size_t)max_tx * (size_t)max_ty * 9 + 255) / 256 * 256) + 256;
+    const size_t fused = (size_t)n_pairs * (size_t)max_tx * (size_t)((max_ty + 15) / 16) * 4 + 256;
+    return two_pass > fused ? two_pass : fused;
   }
   size_t per = 2 * dtw_series_doubles(mt, D) * sizeof(double) + 3 * (size_t)max_tx * sizeof(double);
   per += dtw_fast_cells_bound(max_tx, max_ty, radius) * sizeof(double);  // cost buffer of one level
@@ -848,6 +1040,34 @@ extern "C" int nnk_dtw_align(const nnk_dtw_args_t* a, void* stream) {
   int dev = 0, max_smem = 0;
   NNK_CUDA_CHECK(cudaGetDevice(&dev));
   NNK_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (full && !dtw_force_two_pass() && dtw_fused_ok(a->max_ty, a->D, (size_t)max_smem)) {
+    DtwFusedParams f;
+    f.X = a->X; f.Y = a->Y; f.x_pair_stride = a->x_pair_stride; f.y_pair_stride = a->y_pair_stride;
+    f.x_ld = a->x_ld; f.y_ld = a->y_ld; f.D = a->D; f.len_x = a->len_x; f.len_y = a->len_y; f.order = a->order;
+    f.cost_kind = a->cost_kind; f.path_i = a->path_i; f.path_j = a->path_j; f.path_ld = a->path_ld;
+    f.path_len = a->path_len; f.dist = a->dist; f.cells = (long long*)a->cells; f.max_tx = a->max_tx; f.max_ty = a->max_ty;
+    f.bp = reinterpret_cast<uint32_t*>(a->workspace);
+    f.wpr = (a->max_ty + 15) / 16;
+    f.logdb = p.logdb;
+    const size_t fsmem = dtw_fused_smem(a->max_ty, a->D);
+    const int nb8 = a->D / 8;
+#define NNK_FUSED(TT_, NB_)                                                                                         \
+  do {                                                                                                              \
+    NNK_CUDA_CHECK(cudaFuncSetAttribute(dtw_fused_kernel<TT_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
+    dtw_fused_kernel<TT_, NB_><<<a->n_pairs, DTW_FR, fsmem, st>>>(f);                                               \
+  } while (0)
+    if (a->dtype == NNK_F64) {
+      switch (nb8) { case 1: NNK_FUSED(double, 1); break; case 2: NNK_FUSED(double, 2); break; case 3: NNK_FUSED(double, 3); break;
+                     default: NNK_FUSED(double, 4); }
+    } else {
+      switch (nb8) { case 1: NNK_FUSED(float, 1); break; case 2: NNK_FUSED(float, 2); break; case 3: NNK_FUSED(float, 3); break;
+                     default: NNK_FUSED(float, 4); }
+    }
+#undef NNK_FUSED
+    count_launch();
+    NNK_CUDA_CHECK(cudaGetLastError());
+    return NNK_OK;
+  }
   if (full) {
     const size_t smem = sizeof(double) * 3 * (size_t)a->max_tx + 16;
     NNK_REQUIRE(smem <= (size_t)max_smem, NNK_ERR_UNSUPPORTED, "sequence too long for the wavefront buffers in shared memory");

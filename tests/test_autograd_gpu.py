@@ -229,7 +229,7 @@ def test_unit_variance_factored_sweeps_match_dense(sd, T, reshaped, nwin):
     (gx,) = torch.autograd.grad(y, x, o)
     Rd = R.double()
     for b in range(B):
-        xr = mu[b].double().view(T, nwin, sd).transpose(0, 1).reshape(nwin * T, sd)
+        xr = mu[b].detach().double().view(T, nwin, sd).transpose(0, 1).reshape(nwin * T, sd)
         yref = Rd @ xr
         assert rel_err(y[b].detach().cpu().numpy(), yref.cpu().numpy()) < 2e-6
         gref = Rd.t() @ o[b].double()  # (nw*T, sd)
