@@ -88,8 +88,9 @@ def config_cfg5(n_gpus):
     return {
         "workload": "configs[4]: %d-utterance paramgen.mlpg batch, T~U{%d..%d} (9.0e6 frames), D=187 Merlin layout, 3 windows, "
                     "per-frame diagonal variances, float32 I/O, STRONG-scaled over %d GPU(s): ShardPlan (%d buckets, "
-                    "longest-first greedy per bucket), inputs pre-sharded in HBM, per bucket solve -> in-place NCCL "
-                    "all_gather_into_tensor overlapped with the next bucket; every rank ends with all trajectories"
+                    "longest-first greedy per bucket), inputs pre-sharded in HBM, per bucket solve -> in-place "
+                    "all-gather (copy-engine pushes into IPC-shared peer buffers over NVLink; NNK_SHARD_TRANSPORT=nccl: NCCL "
+                    "all_gather_into_tensor) overlapped with the next bucket; every rank ends with all trajectories"
                     % (CFG5_UTT, CFG5_T_LO, CFG5_T_HI, n_gpus, CFG5_BUCKETS),
         "utterances": CFG5_UTT, "static_dims": 62, "windows": 3, "buckets": CFG5_BUCKETS,
         "sharding": "utterance-sharded, %d rank(s), %d bucketed all-gathers per pass (the path's only collective)"
@@ -308,7 +309,7 @@ def profile_traffic(patterns):
 class Cfg5Pass(object):
     """configs[4] resident on this rank in ShardPlan layout + one timed pass over it."""
 
-    def __init__(self, rank, world, device):
+    def __init__(self, rank, world, device, transport=None):
         import torch
         from nnmnkwii_b200 import paramgen as G
         from nnmnkwii_b200 import sharding
@@ -316,7 +317,8 @@ class Cfg5Pass(object):
         self.lens = cfg5_lengths()
         self.layout = G.merlin_layout()
         self.plan = sharding.ShardPlan(self.lens, world, CFG5_BUCKETS)
-        self.batch = sharding.ShardedBatch(self.plan, rank, device, D_IN, D_OUT, torch.float32)
+        self.transport = transport if world > 1 else None
+        self.batch = sharding.ShardedBatch(self.plan, rank, device, D_IN, D_OUT, torch.float32, transport=self.transport)
         for b in range(self.plan.n_buckets):  # inputs are generated straight into the rank's HBM slice
             for u in self.plan.members[b][rank]:
                 m, v = cfg5_utterance(u, self.lens[u], device)
@@ -341,7 +343,17 @@ class Cfg5Pass(object):
             sharding._solve_bucket(self.batch, b, wc, chains, self.layout.n_chain, self.status)
 
     def gather_only(self, group=None):
+        import torch
         from nnmnkwii_b200 import sharding
+        if self.batch.peer is not None:
+            cur = torch.cuda.current_stream(self.device)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            for b in range(self.plan.n_buckets):
+                n_rows = int(self.plan.lengths[self.plan.members[b][self.rank]].sum())
+                self.batch.peer.push(self.plan.goff[b] + self.rank * self.plan.cap[b], n_rows, ev)
+            self.batch.peer.finish(cur)
+            return
         works = [sharding._gather_bucket(self.batch.result, self.plan, b, self.rank, group) for b in range(self.plan.n_buckets)]
         for w in works:
             if w is not None:
@@ -387,7 +399,9 @@ def run_sharded(args, rank, world, local):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
-    job = Cfg5Pass(rank, world, device)
+    from nnmnkwii_b200 import sharding
+    transport = sharding.default_transport(device)
+    job = Cfg5Pass(rank, world, device, transport)
 
     def barrier():
         dist.barrier()
@@ -447,6 +461,9 @@ def run_sharded(args, rank, world, local):
     launches += _lib.launch_count() - n1
     e2e_val = job.frames_total * e2e_steps / e2e_s
     h2d = reduce_max(float(hm.nbytes + hv.nbytes))
+    barrier()
+    if job.batch.peer is not None:
+        job.batch.peer.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank != 0:
@@ -464,7 +481,7 @@ def run_sharded(args, rank, world, local):
         "gpu_launches": int(launches),
         "kernel_ms": kernel_ms, "allgather_ms": gather_ms, "allgather_exposed_ms": max(0.0, pass_ms - kernel_ms),
         "kernel_plus_allgather_ms": kernel_ms + gather_ms,
-        "allgather": {"bytes_received_per_rank": int(out_bytes * (world - 1) / world), "buckets": job.plan.n_buckets,
+        "allgather": {"transport": transport, "bytes_received_per_rank": int(out_bytes * (world - 1) / world), "buckets": job.plan.n_buckets,
                       "alone_gbs_per_rank": out_bytes * (world - 1) / world / (gather_ms * 1e-3) / 1e9,
                       "note": "every rank must RECEIVE (N-1)/N of the 2.27 GB result per pass: at N=8 that is 1.98 GB over one "
                               "NVLink port (<= 900 GB/s/dir) >= 2.2 ms against ~1.05 ms of solve -- the pass is NVLink-receive "

@@ -250,6 +250,18 @@ int nnk_segment_copy(const void* src, void* dst, int32_t elem_bytes, int64_t col
                      const int64_t* src_row, const int64_t* dst_row, const int32_t* len, int32_t n_seg,
                      int32_t max_len, void* stream);
 
+/* Peer-memory transport of a sharded result (one process per GPU of one NVLink / NVSwitch box):
+ * a cudaMalloc allocation per rank, shared through CUDA IPC handles; nnk_peer_copy pushes a byte range
+ * into a peer's mapping with copy-engine DMA over NVLink (no SMs: it overlaps the solve kernels, which
+ * an NCCL all-gather kernel cannot while they hold every SM slot).  The 64-byte handle travels between
+ * the processes by any host channel (torch.distributed here).                                       */
+int nnk_peer_alloc(size_t bytes, void** ptr);
+int nnk_peer_free(void* ptr);
+int nnk_peer_export(const void* ptr, unsigned char* handle64);
+int nnk_peer_open(const unsigned char* handle64, void** ptr);
+int nnk_peer_close(void* ptr);
+int nnk_peer_copy(void* dst_peer, const void* src_local, size_t bytes, void* stream);
+
 const char* nnk_last_error(void);
 int nnk_abi_version(void);
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches).       */

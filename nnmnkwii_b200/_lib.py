@@ -96,6 +96,7 @@ EXPORTS = [
     "nnk_uv_band_profile", "nnk_uv_band_extract", "nnk_uv_apply", "nnk_uv_apply_toeplitz", "nnk_uv_apply_factored",
     "nnk_dtw_align", "nnk_dtw_workspace_bytes", "nnk_gather_rows", "nnk_trim_lengths", "nnk_delta_features",
     "nnk_metric_workspace_bytes", "nnk_frame_metric", "nnk_f0_metric", "nnk_segment_copy",
+    "nnk_peer_alloc", "nnk_peer_free", "nnk_peer_export", "nnk_peer_open", "nnk_peer_close", "nnk_peer_copy",
 ]
 
 
@@ -156,6 +157,11 @@ def _load():
     L.nnk_frame_metric.argtypes = [vp, vp, i32, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, i64, vp]
     L.nnk_f0_metric.restype = ctypes.c_int
     L.nnk_f0_metric.argtypes = [vp, vp, vp, vp, i32, i32, i32, i64, i64, vp, i32, vp, vp, vp, i64, vp]
+    for name, args in (("nnk_peer_alloc", [ctypes.c_size_t, ctypes.POINTER(vp)]), ("nnk_peer_free", [vp]),
+                       ("nnk_peer_export", [vp, vp]), ("nnk_peer_open", [vp, ctypes.POINTER(vp)]), ("nnk_peer_close", [vp]),
+                       ("nnk_peer_copy", [vp, vp, ctypes.c_size_t, vp])):
+        getattr(L, name).restype = ctypes.c_int
+        getattr(L, name).argtypes = args
     L.nnk_segment_copy.restype = ctypes.c_int
     L.nnk_segment_copy.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, vp, i32, i32, vp]
     return L

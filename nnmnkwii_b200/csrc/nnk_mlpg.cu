@@ -29,6 +29,10 @@
 #define NNK_AS_NA 3
 #define NNK_AS_NSA 1
 #endif
+// depth of the band-row (PB) ring in tiles; must be >= the producers' tile stride (see nnk_mlpg_as.cuh)
+#ifndef NNK_AS_ND
+#define NNK_AS_ND (NNK_AS_PAIRS ? 6 : 4)
+#endif
 
 namespace nnk {
 
@@ -367,7 +371,7 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   constexpr int ES = (int)sizeof(Tin);
   constexpr bool GRAD = (MODE == MODE_GRAD);
   constexpr bool GRAD_MODE = GRAD;
-  constexpr int TT = 4, NS = 4, TTB = 4, NA = NNK_AS_NA, NSA = NNK_AS_NSA, ND = 4;
+  constexpr int TT = 4, NS = 4, TTB = 4, NA = NNK_AS_NA, NSA = NNK_AS_NSA, ND = NNK_AS_ND;
   // backward-sweep scratch ring of the paired kernel: 64 frames in flight (32 when the variance rows ride along)
   constexpr int TTB_AS = 8, NSB_AS = GRAD_MODE ? 4 : 8;
   AsGeom as_geom;

@@ -20,6 +20,12 @@
 #pragma once
 #include "nnk_mlpg_tma.cuh"
 
+// assemblers own PAIRS of consecutive tiles and carry the converted window halo from the first to the
+// second tile of a pair in registers (10 instead of 12 conversions per 8 frames, 17 % fewer staged rows)
+#ifndef NNK_AS_PAIRS
+#define NNK_AS_PAIRS 0
+#endif
+
 namespace nnk {
 
 struct AsGeom {
@@ -62,6 +68,16 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   constexpr int ES = (int)sizeof(Tin);
   constexpr bool GRAD = (MODE == MODE_GRAD);
   static_assert(MODE == MODE_FWD || MODE == MODE_GRAD, "staged kernel: forward or gradient");
+  // PB-ring protocol invariant (root cause of the parked paired-tiles deadlock, tools/experiments/README.md):
+  // an mbarrier wait only sees the PARITY of a phase, so a producer that gets two ring wraps ahead of the
+  // consumer would pass its pb_empty wait on a stale phase and overwrite an undrained slot.  A producer's
+  // wait for tile k proves that tile k - ND has been drained; its next tile is k + NA, which needs tile
+  // k + NA - 2 ND drained to be alias-free -- guaranteed (the solver drains in order) iff NA <= ND.
+  // With PAIRS (an assembler owns tiles 2q, 2q+1 and next 2q + 2 NA, 2q + 2 NA + 1) the largest stride is
+  // 2 NA - 1: the round-1 attempt ran it with ND = 4 < 5, which is exactly the timing-dependent deadlock
+  // that showed up under pytest / bench.py but not stand-alone.
+  constexpr bool PAIRS = (NNK_AS_PAIRS != 0) && (NT > 1);
+  static_assert((PAIRS ? 2 * NA - 1 : NA) <= ND, "producer tile stride must not exceed the PB ring depth (parity aliasing)");
   extern __shared__ __align__(128) unsigned char smem[];
   // barriers: input full [NA][NSA] | PB full [ND] | PB empty [ND] | scratch full [NSB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -74,7 +90,15 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   double* pb = reinterpret_cast<double*>(smem + g.off_pb);          // [ND][TT][NR][32]
 
   const int lane = threadIdx.x & 31;
-  const int role = threadIdx.x >> 5;  // 0..NA-1 = assemblers, NA = solver
+  // 0..NA-1 = assemblers, NA = solver.  The hardware deals the warps of a CTA round-robin to the four
+  // SM sub-partitions; with a fixed role per warp index every solver (latency bound, few instructions)
+  // would share one scheduler and the issue-hungry assemblers the other three.  Rotating the roles by
+  // the CTA index gives every scheduler the same mix.
+#ifdef NNK_AS_NO_ROTATE
+  const int role = threadIdx.x >> 5;
+#else
+  const int role = (int)(((threadIdx.x >> 5) + blockIdx.x) % (NA + 1));
+#endif
   const int item = blockIdx.x;
   const int urank = p.urank0 + item / p.n_groups;
   const int grp = item % p.n_groups;
@@ -131,11 +155,24 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
     unsigned char* ring = rings + (size_t)role * g.ring_a;
     uint64_t* my_full = in_full + role * NSA;
 
-    // tile k stages frames [f_lo, f_hi) = [max(0, k*TT - (NT-1)), min(T, k*TT + TT))  (never empty);
+    // Tile ownership.  PAIRS: consecutive tiles (2q, 2q+1) belong to assembler q mod NA; the second
+    // tile of a pair re-uses the last NT-1 converted frames of the first one (kept in registers)
+    // instead of staging and converting its window halo again: 2*TT + NT-1 conversions per pair
+    // instead of 2*(TT + NT-1).  Otherwise tile k belongs to assembler k mod NA and every tile is
+    // self-contained.
+    constexpr int NH = (NT > 1) ? NT - 1 : 1;  // halo slots carried between the tiles of a pair
+    auto next_tile = [&](int k) { return PAIRS ? (((k & 1) == 0) ? k + 1 : k - 1 + 2 * NA) : k + NA; };
+    auto second = [&](int k) { return PAIRS && (k & 1); };
+    // tile k stages frames [f_lo, f_hi): its TT own frames, preceded by the halo unless it is a second tile
+    auto tile_flo = [&](int k) { return second(k) ? k * TT : max(0, k * TT - (NT - 1)); };
+    auto tile_fhi = [&](int k) { return min(T, k * TT + TT); };
+    // (only the last tile of a chain can have no frame of its own; it is then a second tile and stages nothing)
+
     // PREF: only pull the two ranges into L2 (issued PFD turns of this warp ahead of the real copy)
     auto issue_in = [&](auto pref_tag, int k, int s) {  // lane 0 only
       constexpr bool PREF = decltype(pref_tag)::value;
-      const int f_lo = max(0, k * TT - (NT - 1)), f_hi = min(T, k * TT + TT);
+      const int f_lo = tile_flo(k), f_hi = tile_fhi(k);
+      if (k >= npb || f_lo >= f_hi) return;
       const uint64_t A0 = g_m + (uint64_t)((int64_t)f_lo * ldb_m);
       const uint64_t a0 = A0 & ~(uint64_t)15;
       const uint32_t nb = (uint32_t)(((A0 + (uint64_t)((f_hi - f_lo - 1) * (int64_t)ldb_m) + span_m + 15) & ~(uint64_t)15) - a0);
@@ -156,11 +193,11 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
       if (!VARG) bulk_g2s(ring + (size_t)s * 2 * g.sb_in + g.sb_in, reinterpret_cast<const void*>(b0), nb2, my_full + s);
     };
     constexpr int PFD = 2;  // L2 prefetch distance in turns of this warp beyond its staged tiles
+    const int k_first = PAIRS ? 2 * role : role;
     if (lane == 0) {
-      for (int i = 0; i < NSA; ++i)
-        if (role + i * NA < npb) issue_in(FullTile<false>{}, role + i * NA, i);
-      for (int i = NSA; i < NSA + PFD; ++i)
-        if (role + i * NA < npb) issue_in(FullTile<true>{}, role + i * NA, 0);
+      int k = k_first;
+      for (int i = 0; i < NSA; ++i, k = next_tile(k)) issue_in(FullTile<false>{}, k, i);
+      for (int i = 0; i < PFD; ++i, k = next_tile(k)) issue_in(FullTile<true>{}, k, 0);
     }
 
     double gtau[NW];
@@ -168,20 +205,38 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
     for (int w = 0; w < NW; ++w)
       gtau[w] = VARG ? recip_in_dtype<Tin>::f(p.vars[my_col + w * my_stride]) : 0.0;
 
-    // convert the NF frames of tile k (slot j <-> frame k*TT - (NT-1) + j; staged row = frame - f_lo),
-    // assemble its TT band rows and publish them to PB slot `dst`
-    auto do_tile = [&](auto full_tag, int k, const unsigned char* sm_m, const unsigned char* sm_v, double* dst, int stage) {
+    // the last NH converted frames of the previous tile of this warp (used by second tiles)
+    double cft[NH][NW], cfm[NH][NW];
+    float cfg[NH];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+      cfg[j] = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { cft[j][w] = 0.0; cfm[j][w] = 0.0; }
+    }
+
+    // convert the frames of tile k (slot j <-> frame k*TT - (NT-1) + j; staged row = frame - f_lo; SECOND:
+    // slots 0 .. NT-2 come from the carry), assemble its TT band rows and publish them to PB slot `dst`
+    auto do_tile = [&](auto full_tag, auto second_tag, int k, const unsigned char* sm_m, const unsigned char* sm_v,
+                       double* dst, int stage) {
       constexpr bool FULL = decltype(full_tag)::value;
+      constexpr bool SECOND = decltype(second_tag)::value;
       const int fbase = k * TT - (NT - 1);
-      const int f_lo = max(0, fbase);
+      const int f_lo = SECOND ? k * TT : max(0, fbase);
       double ft[NF][NW], fm[NF][NW];
       float fg[NF];  // GRAD: grad_out of this lane's chain
 #pragma unroll
       for (int j = 0; j < NF; ++j) {
+        if (SECOND && j < NT - 1) {
+          fg[j] = cfg[j];
+#pragma unroll
+          for (int w = 0; w < NW; ++w) { ft[j][w] = cft[j][w]; fm[j][w] = cfm[j][w]; }
+          continue;
+        }
         const int f = fbase + j;
         const bool real = FULL || (f >= 0 && f < T);
         const bool edge = !FULL && ((m_edge == 0) || (f < m_edge) || (f >= T - m_edge));
-        const int row = real ? (FULL ? j : f - f_lo) : 0;
+        const int row = real ? (FULL ? (SECOND ? j - (NT - 1) : j) : f - f_lo) : 0;
         Tin mraw[NW];
         if (GRAD) {
           fg[j] = *reinterpret_cast<const float*>(sm_m + row * ldb_m + colg);
@@ -202,14 +257,27 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
           else tw = recip_fast<Tin>::f(*reinterpret_cast<const Tin*>(sm_v + row * ldb_v + colb[w]));
           if (!FULL) tw = (!real || (w > 0 && edge)) ? 0.0 : tw;
           ft[j][w] = tw;
-          fm[j][w] = tw * (double)mraw[w];
+          fm[j][w] = (FULL || real) ? tw * (double)mraw[w] : 0.0;
+        }
+      }
+      if (PAIRS && !SECOND) {
+#pragma unroll
+        for (int j = 0; j < NH; ++j) {
+          cfg[j] = fg[TT + j];
+#pragma unroll
+          for (int w = 0; w < NW; ++w) { cft[j][w] = ft[TT + j][w]; cfm[j][w] = fm[TT + j][w]; }
         }
       }
       // the staged rows now live in registers: refill this stage before assembling / publishing
       __syncwarp();
       if (lane == 0) {
-        if (k + NSA * NA < npb) issue_in(FullTile<false>{}, k + NSA * NA, stage);
-        if (k + (NSA + PFD) * NA < npb) issue_in(FullTile<true>{}, k + (NSA + PFD) * NA, 0);
+        int kn = k;
+#pragma unroll
+        for (int i = 0; i < NSA; ++i) kn = next_tile(kn);
+        issue_in(FullTile<false>{}, kn, stage);
+#pragma unroll
+        for (int i = 0; i < PFD; ++i) kn = next_tile(kn);
+        issue_in(FullTile<true>{}, kn, 0);
       }
 #pragma unroll
       for (int j = 0; j < TT; ++j) {
@@ -252,25 +320,32 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
 #ifdef NNK_AS_PROF
     long long prof[4] = {0, 0, 0, 0};
 #endif
-    for (int k = role; k < npb; k += NA) {
+    for (int k = k_first; k < npb; k = next_tile(k)) {
       const int ps = k % ND;
+      const int f_lo = tile_flo(k);
+      const bool staged_rows = f_lo < tile_fhi(k);
       AS_TICK(c0);
       mbar_wait_parked(pb_empty + ps, (uint32_t)(((k / ND) & 1) ^ 1));  // the solver has drained this PB slot
       AS_TICK(c1);
-      mbar_wait(my_full + s, par);
+      if (staged_rows) mbar_wait(my_full + s, par);
       AS_TICK(c2);
       AS_ACC(0, c0, c1);
       AS_ACC(1, c1, c2);
       double* dst = pb + (size_t)ps * (TT * NR * 32);
-      const int f_lo = max(0, k * TT - (NT - 1));
       const uint32_t mis_m = (uint32_t)((g_m + (uint64_t)((int64_t)f_lo * ldb_m)) & 15);
       const uint32_t mis_v = (uint32_t)((g_v + (uint64_t)((int64_t)f_lo * ldb_v)) & 15);
       const unsigned char* sm_m = ring + (size_t)s * 2 * g.sb_in + mis_m;
       const unsigned char* sm_v = ring + (size_t)s * 2 * g.sb_in + g.sb_in + mis_v;
-      if (m_edge > 0 && k * TT - (NT - 1) >= m_edge && k * TT + TT <= T - m_edge) do_tile(FullTile<true>{}, k, sm_m, sm_v, dst, s);
-      else do_tile(FullTile<false>{}, k, sm_m, sm_v, dst, s);
+      const bool full = m_edge > 0 && k * TT - (NT - 1) >= m_edge && k * TT + TT <= T - m_edge;
+      if (second(k)) {
+        if (full) do_tile(FullTile<true>{}, FullTile<PAIRS>{}, k, sm_m, sm_v, dst, s);
+        else do_tile(FullTile<false>{}, FullTile<PAIRS>{}, k, sm_m, sm_v, dst, s);
+      } else {
+        if (full) do_tile(FullTile<true>{}, FullTile<false>{}, k, sm_m, sm_v, dst, s);
+        else do_tile(FullTile<false>{}, FullTile<false>{}, k, sm_m, sm_v, dst, s);
+      }
       mbar_arrive(pb_full + ps);  // release: this lane's rows are visible to the solver
-      if (++s == NSA) { s = 0; par ^= 1; }
+      if (staged_rows && ++s == NSA) { s = 0; par ^= 1; }
       AS_TICK(c3);
       AS_ACC(2, c2, c3);
     }

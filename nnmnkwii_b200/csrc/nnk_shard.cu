@@ -3,6 +3,8 @@
 // (row segments) between two row-major matrices, e.g. back into the caller's utterance order.
 // Pure data movement, HBM bound: every segment row is read once and written once with 16-byte
 // accesses when the row pitch allows, 4-byte words otherwise.
+#include <string.h>
+
 #include "nnk_common.cuh"
 
 namespace nnk {
@@ -60,5 +62,53 @@ extern "C" int nnk_segment_copy(const void* src, void* dst, int32_t elem_bytes, 
   else segment_copy_kernel<uint32_t><<<grid, 256, 0, st>>>(p);
   count_launch();
   NNK_CUDA_CHECK(cudaGetLastError());
+  return NNK_OK;
+}
+
+// ---- peer-memory transport of the sharded result (one process per GPU, NVLink / NVSwitch) -----------------
+// The all-gather of the trajectories does not need SMs at all: every rank PUSHES its slot of the result
+// buffer into the same slot of every peer's buffer with copy-engine DMA over NVLink (cudaMemcpyAsync
+// between peer-mapped allocations).  Unlike an NCCL kernel, which has to wait for SM slots the solve
+// kernel holds, the copies run while the next bucket is being solved.  The buffers are plain cudaMalloc
+// allocations shared between the per-GPU processes through CUDA IPC handles.
+extern "C" int nnk_peer_alloc(size_t bytes, void** ptr) {
+  NNK_REQUIRE(ptr != nullptr && bytes > 0, NNK_ERR_ARG, "bad argument");
+  NNK_CUDA_CHECK(cudaMalloc(ptr, bytes));
+  NNK_CUDA_CHECK(cudaMemset(*ptr, 0, bytes));
+  return NNK_OK;
+}
+
+extern "C" int nnk_peer_free(void* ptr) {
+  if (ptr) NNK_CUDA_CHECK(cudaFree(ptr));
+  return NNK_OK;
+}
+
+extern "C" int nnk_peer_export(const void* ptr, unsigned char* handle64) {
+  NNK_REQUIRE(ptr && handle64, NNK_ERR_ARG, "NULL pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  NNK_CUDA_CHECK(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+  memcpy(handle64, &h, 64);
+  return NNK_OK;
+}
+
+extern "C" int nnk_peer_open(const unsigned char* handle64, void** ptr) {
+  NNK_REQUIRE(ptr && handle64, NNK_ERR_ARG, "NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  NNK_CUDA_CHECK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return NNK_OK;
+}
+
+extern "C" int nnk_peer_close(void* ptr) {
+  if (ptr) NNK_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+  return NNK_OK;
+}
+
+extern "C" int nnk_peer_copy(void* dst_peer, const void* src_local, size_t bytes, void* stream) {
+  NNK_REQUIRE(dst_peer && src_local, NNK_ERR_ARG, "NULL pointer");
+  if (bytes == 0) return NNK_OK;
+  DeviceGuard guard(src_local);
+  NNK_CUDA_CHECK(cudaMemcpyAsync(dst_peer, src_local, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return NNK_OK;
 }

@@ -385,16 +385,72 @@ __device__ __forceinline__ void uv_st2(float* p, float2 v, bool ok0, bool ok1) {
 
 constexpr int UVF_TTU = 8;  // outputs of the long filter per register block
 
+// rows outside the shift-invariant interval (the ~K rows next to each end) use the per-row band table
+// `tab` ([T][nw][2K+1]); they are handled by extra CTAs of the SAME launch (blockIdx.x >= n_tiles), one
+// row per warp, so that a sweep is a single kernel.  forward: y[t] = sum_w sum_j tab[t][w][j] x_w[t+j-K];
+// backward: g_w[s] = sum_j tab[s][w][j] o[s+j-K].
+template <bool BWD, bool VEC>
+__device__ __forceinline__ void uv_edge_rows(const float* __restrict__ tab, const float* __restrict__ x, float* __restrict__ y,
+                                             int Tn, int sd, int nw, int K, int t_lo, int t_hi, int reshaped, int eblk) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int t = eblk * 4 + warp;          // index among the edge rows: [0, t_lo) then [t_hi, Tn)
+  if (t >= t_lo) t += t_hi - t_lo;
+  if (t >= Tn) return;
+  const int d = 2 * (blockIdx.y * 32 + lane);
+  const bool ok0 = d < sd, ok1 = d + 1 < sd;
+  const int b = blockIdx.z;
+  const int W = 2 * K + 1;
+  const int j_lo = max(0, K - t), j_hi = min(2 * K, Tn - 1 - t + K);
+  const int64_t nwsd = (int64_t)nw * sd;
+  if (!BWD) {
+    const float* xb = x + (int64_t)b * Tn * nwsd + d;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int w = 0; w < nw; ++w) {
+      const float* coef = tab + ((int64_t)t * nw + w) * W;
+      for (int j = j_lo; j <= j_hi; ++j) {
+        const float c = __ldg(coef + j);
+        const int s = t + j - K;
+        const int64_t off = reshaped ? ((int64_t)w * Tn + s) * sd : (int64_t)s * nwsd + (int64_t)w * sd;
+        const float2 v = uv_ld2<VEC>(xb + off, ok0, ok1);
+        acc.x = fmaf(c, v.x, acc.x);
+        acc.y = fmaf(c, v.y, acc.y);
+      }
+    }
+    uv_st2<VEC>(y + ((int64_t)b * Tn + t) * sd + d, acc, ok0, ok1);
+  } else {
+    const float* gb = x + (int64_t)b * Tn * sd + d;
+    float* ob = y + (int64_t)b * Tn * nwsd + d;
+    for (int w = 0; w < nw; ++w) {
+      const float* coef = tab + ((int64_t)t * nw + w) * W;
+      float2 acc = make_float2(0.f, 0.f);
+      for (int j = j_lo; j <= j_hi; ++j) {
+        const float c = __ldg(coef + j);
+        const float2 v = uv_ld2<VEC>(gb + (int64_t)(t + j - K) * sd, ok0, ok1);
+        acc.x = fmaf(c, v.x, acc.x);
+        acc.y = fmaf(c, v.y, acc.y);
+      }
+      const int64_t off = reshaped ? ((int64_t)w * Tn + t) * sd : (int64_t)t * nwsd + (int64_t)w * sd;
+      uv_st2<VEC>(ob + off, acc, ok0, ok1);
+    }
+  }
+}
+
 // forward: tile of TC output frames; stage 1 fills sb[p] = b[t0 - KK + p], p < TC + 2 KK
 template <int KK, int KC, int NWT, int TC, bool VEC>
-__global__ void __launch_bounds__(128) uv_fact_fwd_kernel(const __grid_constant__ UvFactTaps<KK, KC, NWT> taps,
-                                                          const float* __restrict__ x, float* __restrict__ y, int Tn, int sd,
-                                                          int nw, int t_lo, int t_hi, int reshaped) {
+__global__ void __launch_bounds__(128, 6) uv_fact_fwd_kernel(const __grid_constant__ UvFactTaps<KK, KC, NWT> taps,
+                                                          const float* __restrict__ tab, const float* __restrict__ x,
+                                                          float* __restrict__ y, int Tn, int sd, int nw, int K, int t_lo, int t_hi,
+                                                          int reshaped, int n_tiles) {
   constexpr int NP = TC + 2 * KK;      // intermediate positions of the tile
   constexpr int PW = NP / 4;           // ... per warp
-  constexpr int CH = 4;                // stage-1 positions per register block
-  static_assert(NP % 4 == 0 && PW % CH == 0 && TC % (4 * UVF_TTU) == 0, "tile geometry");
+  constexpr int NBLK = 4;              // stage-1 register blocks per warp (unrolled: the loads of a block overlap
+  constexpr int CH = PW / NBLK;        //   the multiply-adds of the previous one)
+  static_assert(NP % (4 * NBLK) == 0 && TC % (4 * UVF_TTU) == 0, "tile geometry");
   extern __shared__ __align__(16) float2 sb[];  // [NP][32]
+  if ((int)blockIdx.x >= n_tiles) {
+    uv_edge_rows<false, VEC>(tab, x, y, Tn, sd, nw, K, t_lo, t_hi, reshaped, (int)blockIdx.x - n_tiles);
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d = 2 * (blockIdx.y * 32 + lane);
   const bool ok0 = d < sd, ok1 = d + 1 < sd;
@@ -402,28 +458,38 @@ __global__ void __launch_bounds__(128) uv_fact_fwd_kernel(const __grid_constant_
   const int t0 = t_lo + blockIdx.x * TC;
   const int64_t nwsd = (int64_t)nw * sd;
   const float* xb = x + (int64_t)b * Tn * nwsd + d;
+  const int64_t fstep = reshaped ? (int64_t)sd : nwsd;  // elements between consecutive frames of one window
   // ---- stage 1: short stencils -> b ----
-#pragma unroll 1
-  for (int blk = 0; blk < PW / CH; ++blk) {
-    const int p0 = warp * PW + blk * CH;
-    const int s0 = t0 - KK + p0;  // first position of the block
+#pragma unroll
+  for (int half = 0; half < NBLK; ++half) {
+    const int p0 = warp * PW + half * CH;
+    const int f0 = t0 - KK + p0 - KC;  // first input frame of the block
+    const bool interior = (f0 >= 0) && (f0 + CH + 2 * KC <= Tn);
     float2 acc[CH];
 #pragma unroll
     for (int i = 0; i < CH; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int w = 0; w < NWT; ++w) {
       if (w < nw) {
+        const float* pw = xb + (reshaped ? (int64_t)w * Tn * sd : (int64_t)w * sd);
+        float2 v[CH + 2 * KC];
+        if (interior) {
 #pragma unroll
-        for (int r = 0; r < CH + 2 * KC; ++r) {  // frame s0 - KC + r feeds position i with tap k = r - i
-          const int s = s0 - KC + r;
-          const bool in = (s >= 0 && s < Tn);
-          const int sc = in ? s : 0;
-          const int64_t off = reshaped ? ((int64_t)w * Tn + sc) * sd : (int64_t)sc * nwsd + (int64_t)w * sd;
-          const float2 v = uv_ld2<VEC>(xb + off, ok0 && in, ok1 && in);
+          for (int r = 0; r < CH + 2 * KC; ++r) v[r] = uv_ld2<VEC>(pw + (int64_t)(f0 + r) * fstep, ok0, ok1);
+        } else {
+#pragma unroll
+          for (int r = 0; r < CH + 2 * KC; ++r) {
+            const int f = f0 + r;
+            const bool in = (f >= 0 && f < Tn);
+            v[r] = uv_ld2<VEC>(pw + (int64_t)(in ? f : 0) * fstep, ok0 && in, ok1 && in);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < CH + 2 * KC; ++r) {  // frame f0 + r feeds position i with tap k = r - i
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const int k = r - i;
-            if (k >= 0 && k <= 2 * KC) acc[i] = __ffma2_rn(taps.c[w][k], v, acc[i]);
+            if (k >= 0 && k <= 2 * KC) acc[i] = __ffma2_rn(taps.c[w][k], v[r], acc[i]);
           }
         }
       }
@@ -462,10 +528,15 @@ __global__ void __launch_bounds__(128) uv_fact_fwd_kernel(const __grid_constant_
 // inputs from global / L1); stage 2 applies the short stencils and writes the nw gradient streams
 template <int KK, int KC, int NWT, bool VEC>
 __global__ void __launch_bounds__(128) uv_fact_bwd_kernel(const __grid_constant__ UvFactTaps<KK, KC, NWT> taps,
-                                                          const float* __restrict__ go, float* __restrict__ gx, int Tn, int sd,
-                                                          int nw, int t_lo, int t_hi, int reshaped) {
+                                                          const float* __restrict__ tab, const float* __restrict__ go,
+                                                          float* __restrict__ gx, int Tn, int sd, int nw, int K, int t_lo, int t_hi,
+                                                          int reshaped, int n_tiles) {
   constexpr int NP = 64, TC = NP - 2 * KC, PW = NP / 4;
   __shared__ __align__(16) float2 sa[NP * 32];
+  if ((int)blockIdx.x >= n_tiles) {
+    uv_edge_rows<true, VEC>(tab, go, gx, Tn, sd, nw, K, t_lo, t_hi, reshaped, (int)blockIdx.x - n_tiles);
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d = 2 * (blockIdx.y * 32 + lane);
   const bool ok0 = d < sd, ok1 = d + 1 < sd;
@@ -531,8 +602,8 @@ __global__ void __launch_bounds__(128) uv_fact_bwd_kernel(const __grid_constant_
 }
 
 template <int KK, int KC>
-static int uv_fact_launch(const float* h0, const float* c, const float* x, float* y, int B, int Tn, int sd, int nw, int K,
-                          int kc, int t_lo, int t_hi, int backward, int reshaped, cudaStream_t st) {
+static int uv_fact_launch(const float* tab, const float* h0, const float* c, const float* x, float* y, int B, int Tn, int sd, int nw,
+                          int K, int kc, int t_lo, int t_hi, int backward, int reshaped, cudaStream_t st) {
   constexpr int NWT = 3;
   UvFactTaps<KK, KC, NWT> taps;
   for (int j = 0; j <= 2 * KK; ++j) {  // pad the long filter to the instantiated half-width
@@ -547,24 +618,37 @@ static int uv_fact_launch(const float* h0, const float* c, const float* x, float
       taps.c[w][k] = make_float2(v, v);
     }
   const int rows = t_hi - t_lo;
+  const int n_edge_blocks = (Tn - rows + 3) / 4;  // edge rows ride along as extra CTAs, one row per warp
   const bool vec = (sd % 2 == 0) && (((uintptr_t)x | (uintptr_t)y) % 8 == 0);
   const unsigned gy = (unsigned)(((sd + 1) / 2 + 31) / 32);
   if (!backward) {
     constexpr int TC = 64;
     constexpr size_t smem = (size_t)(TC + 2 * KK) * 32 * sizeof(float2);
-    dim3 grid((unsigned)((rows + TC - 1) / TC), gy, (unsigned)B);
+    const int n_tiles = (rows + TC - 1) / TC;
+    dim3 grid((unsigned)(n_tiles + n_edge_blocks), gy, (unsigned)B);
+    static bool attr_done[64][2];  // per template instance and device: raise the dynamic shared-memory limit once
+    int dev_id = 0;
+    NNK_CUDA_CHECK(cudaGetDevice(&dev_id));
+    bool* attr_set = attr_done[dev_id & 63];
     if (vec) {
-      NNK_CUDA_CHECK(cudaFuncSetAttribute(uv_fact_fwd_kernel<KK, KC, NWT, TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      uv_fact_fwd_kernel<KK, KC, NWT, TC, true><<<grid, 128, smem, st>>>(taps, x, y, Tn, sd, nw, t_lo, t_hi, reshaped);
+      if (!attr_set[1]) {
+        NNK_CUDA_CHECK(cudaFuncSetAttribute(uv_fact_fwd_kernel<KK, KC, NWT, TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[1] = true;
+      }
+      uv_fact_fwd_kernel<KK, KC, NWT, TC, true><<<grid, 128, smem, st>>>(taps, tab, x, y, Tn, sd, nw, K, t_lo, t_hi, reshaped, n_tiles);
     } else {
-      NNK_CUDA_CHECK(cudaFuncSetAttribute(uv_fact_fwd_kernel<KK, KC, NWT, TC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      uv_fact_fwd_kernel<KK, KC, NWT, TC, false><<<grid, 128, smem, st>>>(taps, x, y, Tn, sd, nw, t_lo, t_hi, reshaped);
+      if (!attr_set[0]) {
+        NNK_CUDA_CHECK(cudaFuncSetAttribute(uv_fact_fwd_kernel<KK, KC, NWT, TC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[0] = true;
+      }
+      uv_fact_fwd_kernel<KK, KC, NWT, TC, false><<<grid, 128, smem, st>>>(taps, tab, x, y, Tn, sd, nw, K, t_lo, t_hi, reshaped, n_tiles);
     }
   } else {
     constexpr int TC = 64 - 2 * KC;
-    dim3 grid((unsigned)((rows + TC - 1) / TC), gy, (unsigned)B);
-    if (vec) uv_fact_bwd_kernel<KK, KC, NWT, true><<<grid, 128, 0, st>>>(taps, x, y, Tn, sd, nw, t_lo, t_hi, reshaped);
-    else uv_fact_bwd_kernel<KK, KC, NWT, false><<<grid, 128, 0, st>>>(taps, x, y, Tn, sd, nw, t_lo, t_hi, reshaped);
+    const int n_tiles = (rows + TC - 1) / TC;
+    dim3 grid((unsigned)(n_tiles + n_edge_blocks), gy, (unsigned)B);
+    if (vec) uv_fact_bwd_kernel<KK, KC, NWT, true><<<grid, 128, 0, st>>>(taps, tab, x, y, Tn, sd, nw, K, t_lo, t_hi, reshaped, n_tiles);
+    else uv_fact_bwd_kernel<KK, KC, NWT, false><<<grid, 128, 0, st>>>(taps, tab, x, y, Tn, sd, nw, K, t_lo, t_hi, reshaped, n_tiles);
   }
   count_launch();
   NNK_CUDA_CHECK(cudaGetLastError());
@@ -665,11 +749,11 @@ extern "C" int nnk_uv_apply_factored(const void* table, const float* h0, const f
   NNK_REQUIRE(B <= 65535 && (sd + 63) / 64 <= 65535, NNK_ERR_ARG, "batch or static_dim too large for one launch");
   DeviceGuard guard(x);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = uv_apply<float>(table, x, y, B, T, sd, nw, K, backward, reshaped, t_lo, t_hi, st);  // edge rows
-  if (rc || t_hi == t_lo) return rc;
+  if (t_hi == t_lo) return uv_apply<float>(table, x, y, B, T, sd, nw, K, backward, reshaped, 0, 0, st);
   const float* xf = (const float*)x;
   float* yf = (float*)y;
-#define NNK_FACT(KV, CV) return uv_fact_launch<KV, CV>(h0, c, xf, yf, B, T, sd, nw, K, KC, t_lo, t_hi, backward, reshaped, st)
+  const float* tf = (const float*)table;
+#define NNK_FACT(KV, CV) return uv_fact_launch<KV, CV>(tf, h0, c, xf, yf, B, T, sd, nw, K, KC, t_lo, t_hi, backward, reshaped, st)
   if (KC <= 1) {
     if (K <= 16) NNK_FACT(16, 1);
     if (K <= 24) NNK_FACT(24, 1);

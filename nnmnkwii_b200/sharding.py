@@ -10,11 +10,19 @@ count, and every group is split over the ranks by a longest-first greedy rule.  
 ``r`` occupies rows ``[goff[b] + r * cap[b], ... + n[b][r])`` of ONE flat ``(rows_total, D_out)``
 result buffer (``cap[b]`` = largest per-rank frame count of the bucket, so the dead rows are at most
 one utterance per bucket and rank -- no per-utterance padding).  The MLPG kernel writes straight into
-that slot (``nnk_mlpg_args_t.out_off``) and the all-gather of bucket ``b`` is the in-place NCCL
-all-gather of the contiguous region ``[goff[b], goff[b] + world * cap[b])``.  The gather of bucket
-``b`` is issued on a side stream as soon as its solve has finished, so it overlaps the solve of
-bucket ``b + 1``; the result stays in shard order with a row table (``ShardedResult.row_start``) and
-is only re-ordered on request (``to_utterance_order``: one segment-copy kernel, no host indexing).
+that slot (``nnk_mlpg_args_t.out_off``) and the all-gather of bucket ``b`` moves the contiguous region
+``[goff[b] + r * cap[b], ...)`` of every rank ``r`` to every other rank.  Two transports:
+
+* ``"peer"`` (default on GPUs): the result buffers are cudaMalloc allocations shared between the per-GPU
+  processes by CUDA IPC; as soon as bucket ``b`` is solved every rank PUSHES its slot into its peers'
+  buffers with copy-engine DMA over NVLink (``nnk_peer_copy``, one side stream per peer).  No SMs are
+  involved, so the transfer really overlaps the solve of bucket ``b + 1`` (an NCCL all-gather kernel has
+  to wait for SM slots that the solve kernel holds -- measured: 80 % of it stayed exposed).  One tiny NCCL
+  all-reduce at the end of the pass is the "everything has landed everywhere" barrier.
+* ``"nccl"`` / gloo: in-place ``all_gather_into_tensor`` of the bucket region, issued on a side stream.
+
+The result stays in shard order with a row table (``ShardedResult.row_start``) and is only re-ordered
+on request (``to_utterance_order``: one segment-copy kernel, no host indexing).
 """
 import ctypes
 
@@ -88,19 +96,101 @@ class ShardPlan(object):
         return int(sum(int(self.lengths[m[rank]].sum()) for m in self.members))
 
 
+class _DeviceBlock(object):
+    """A raw cudaMalloc allocation exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.ptr = ptr
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class PeerTransport(object):
+    """Result buffer of one rank as an IPC-shared cudaMalloc block plus the mapped pointers of every
+    peer's block (see module docstring).  Collective constructor: every rank of ``group`` must call it."""
+
+    def __init__(self, rows, cols, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.group, self.device = group, device
+        self.row_bytes = cols * (4 if dtype == torch.float32 else 8)
+        nbytes = max(1, rows) * self.row_bytes
+        with torch.cuda.device(device):
+            ptr = ctypes.c_void_p()
+            _lib.check(_lib.lib.nnk_peer_alloc(ctypes.c_size_t(nbytes), ctypes.byref(ptr)), "nnk_peer_alloc")
+            self.local_ptr = ptr.value
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.check(_lib.lib.nnk_peer_export(ctypes.c_void_p(self.local_ptr), handle), "nnk_peer_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self.peer_ptr = [None] * self.world
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                out = ctypes.c_void_p()
+                _lib.check(_lib.lib.nnk_peer_open(buf, ctypes.byref(out)), "nnk_peer_open")
+                self.peer_ptr[r] = out.value
+            self.block = _DeviceBlock(self.local_ptr, (max(1, rows), cols), "<f4" if dtype == torch.float32 else "<f8")
+            self.tensor = torch.as_tensor(self.block, device=device)
+            self.streams = [torch.cuda.Stream(device=device) if r != self.rank else None for r in range(self.world)]
+            self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=group)
+
+    def push(self, row0, n_rows, after_event):
+        """Copy rows [row0, row0 + n_rows) of the local block into the same rows of every peer's block
+        (copy engines, one stream per peer), once ``after_event`` (recorded behind the solve) has fired."""
+        from . import _lib
+        off, nbytes = row0 * self.row_bytes, n_rows * self.row_bytes
+        for r in range(self.world):
+            if r == self.rank or nbytes == 0:
+                continue
+            st = self.streams[r]
+            st.wait_event(after_event)
+            _lib.check(_lib.lib.nnk_peer_copy(ctypes.c_void_p(self.peer_ptr[r] + off), ctypes.c_void_p(self.local_ptr + off),
+                                              ctypes.c_size_t(nbytes), ctypes.c_void_p(st.cuda_stream)), "nnk_peer_copy")
+
+    def finish(self, stream):
+        """``stream`` waits for this rank's pushes, then for every other rank's (tiny NCCL all-reduce)."""
+        import torch.distributed as dist
+        for st in self.streams:
+            if st is not None:
+                stream.wait_stream(st)
+        dist.all_reduce(self.flag, group=self.group)
+
+    def close(self):
+        from . import _lib
+        for r, pp in enumerate(self.peer_ptr):
+            if pp:
+                _lib.lib.nnk_peer_close(ctypes.c_void_p(pp))
+        self.peer_ptr = [None] * self.world
+        if self.local_ptr:
+            self.tensor = None
+            _lib.lib.nnk_peer_free(ctypes.c_void_p(self.local_ptr))
+            self.local_ptr = None
+
+
 class ShardedBatch(object):
     """One rank's slice of a sharded batch, resident on its GPU in plan layout: ``means`` /
     ``variances`` ``(rows_local, D)`` (or a global ``(D,)`` variance), per-bucket launch metadata and
-    the flat gathered result buffer."""
+    the flat gathered result buffer (``transport``: "peer" = IPC-shared block, see :class:`PeerTransport`)."""
 
-    def __init__(self, plan, rank, device, D_in, D_out, dtype):
+    def __init__(self, plan, rank, device, D_in, D_out, dtype, transport=None, group=None):
         import torch
 
         self.plan, self.rank, self.device = plan, int(rank), device
         self.D_in, self.D_out, self.dtype = int(D_in), int(D_out), dtype
         self.means = torch.zeros((max(1, plan.rows_local), D_in), dtype=dtype, device=device)
         self.variances = torch.ones((max(1, plan.rows_local), D_in), dtype=dtype, device=device)
-        self.result = torch.zeros((max(1, plan.rows_total), D_out), dtype=dtype, device=device)
+        self.peer = None
+        if transport == "peer" and plan.world > 1:
+            self.peer = PeerTransport(plan.rows_total, D_out, dtype, device, group)
+            self.result = self.peer.tensor
+        else:
+            self.result = torch.zeros((max(1, plan.rows_total), D_out), dtype=dtype, device=device)
         self.meta = []
         for b in range(plan.n_buckets):
             ids = plan.members[b][self.rank]
@@ -226,6 +316,15 @@ def solve_sharded(batch, windows, layout, group=None, comm_stream=None, status=N
                 _gather_bucket(batch.result, plan, b, rank, group)
         return None
     cur = torch.cuda.current_stream(batch.device)
+    if batch.peer is not None:  # copy-engine pushes over NVLink, overlapped with the next bucket's solve
+        for b in range(plan.n_buckets):
+            _solve_bucket(batch, b, wc, chains, layout.n_chain, status)
+            done = torch.cuda.Event()
+            done.record(cur)
+            n_rows = int(plan.lengths[plan.members[b][rank]].sum())
+            batch.peer.push(plan.goff[b] + rank * plan.cap[b], n_rows, done)
+        batch.peer.finish(cur)
+        return None
     if comm_stream is None:
         comm_stream = _comm_stream(batch.device)
     works = []
@@ -254,8 +353,17 @@ def _comm_stream(device):
     return _comm_streams[key]
 
 
+def default_transport(device):
+    """"peer" on CUDA devices unless NNK_SHARD_TRANSPORT=nccl; the collective of the process group otherwise."""
+    import os
+    import torch
+    if torch.device(device).type != "cuda":
+        return None
+    return "nccl" if os.environ.get("NNK_SHARD_TRANSPORT", "peer") == "nccl" else "peer"
+
+
 def mlpg_batch_sharded(means, variances, windows, lengths, layout=None, group=None, device=None, n_buckets=4,
-                       utterance_order=True):
+                       utterance_order=True, transport=None):
     """MLPG over a flat ``(sum_T, D)`` batch sharded by utterance over the ranks of ``group``.
 
     Every rank passes the SAME full host inputs (NumPy) and keeps only its own utterances on its GPU;
@@ -277,7 +385,9 @@ def mlpg_batch_sharded(means, variances, windows, lengths, layout=None, group=No
         device = _default_device()
     dtype = torch.float32 if means.dtype == np.float32 and np.asarray(variances).dtype == np.float32 else torch.float64
     np_dt = np.float32 if dtype == torch.float32 else np.float64
-    batch = ShardedBatch(plan, rank, device, layout.D_in, layout.D_out, dtype)
+    if transport is None:
+        transport = default_transport(device)
+    batch = ShardedBatch(plan, rank, device, layout.D_in, layout.D_out, dtype, transport=transport, group=group)
     batch.load(np.ascontiguousarray(means, dtype=np_dt), np.ascontiguousarray(variances, dtype=np_dt))
     status = torch.zeros(1, dtype=torch.int64, device=device) if batch.result.is_cuda else None
     solve_sharded(batch, windows, layout, group, status=status)
@@ -285,6 +395,13 @@ def mlpg_batch_sharded(means, variances, windows, lengths, layout=None, group=No
         from . import _device as dev
         dev.raise_if_failed(status)
     res = ShardedResult(batch.result, plan)
+    if batch.peer is not None:  # the shared block is released here: hand back tensors that own their memory
+        out = res.to_utterance_order() if utterance_order else ShardedResult(batch.result.clone(), plan)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # nobody may still be pushing into a block that is about to be freed
+        batch.peer.close()
+        batch.result = None
+        return out
     return res.to_utterance_order() if utterance_order else res
 
 

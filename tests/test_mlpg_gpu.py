@@ -391,10 +391,10 @@ def test_deferred_check_surfaces_not_positive_definite():
     import torch
     from nnmnkwii_b200 import _device as dev
     G = _G()
-    ws = windows_set()[2]
-    m = torch.rand(20, 9, device="cuda")
-    v = torch.rand(20, 9, device="cuda") + 0.1
-    v[7, 0] = -1.0  # a negative variance makes a pivot non-positive
+    ws = windows_set()[0]  # static window only: the pivot of frame t is 1 / variance[t]
+    m = torch.rand(20, 3, device="cuda")
+    v = torch.rand(20, 3, device="cuda") + 0.1
+    v[7, 1] = -1.0  # a negative variance makes the 8-th pivot of chain 1 non-positive
     dev.poll_errors(block=True)
     G.mlpg_batch(m, v, ws, lengths=[20], check="deferred")
     with pytest.raises(np.linalg.LinAlgError):

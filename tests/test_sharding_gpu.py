@@ -20,7 +20,11 @@ def _worker(rank, world, port, lens, m, v, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from nnmnkwii_b200 import paramgen as G
     from nnmnkwii_b200.sharding import mlpg_batch_sharded
-    y = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout())
+    y = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout())  # default transport: peer (IPC + copy engines)
+    y2 = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout(), transport="nccl", n_buckets=2)
+    res = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout(), utterance_order=False)
+    y3 = np.concatenate([res.utterance(u).cpu().numpy() for u in range(len(lens))])
+    assert np.array_equal(y.cpu().numpy(), y2.cpu().numpy()) and np.array_equal(y.cpu().numpy(), y3)
     ret[rank] = y.cpu().numpy()
     dist.barrier()
     dist.destroy_process_group()
