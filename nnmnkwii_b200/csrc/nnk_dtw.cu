@@ -800,55 +800,81 @@ __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedPara
     uint32_t* bprow = bp + (size_t)i * p.wpr;
     __syncthreads();  // Ys staged (s == 0) / previous strip's last row complete
     const int nsteps = rows + Ty - 1;
-    for (int k = 0; k < nsteps; ++k) {
-      const int j = k - tid;
-      if (row_ok && j >= 0 && j < Ty) {
-        const double* yr = Ys + (size_t)j * DP;
-        double r8[8];
+    // Rounds of G steps: (A) the local costs of the thread's next G cells -- independent of the recurrence,
+    // G cells in flight per thread so that the long sqrt / reduction chains of one cell overlap the
+    // element-wise work of the next -- then (B) G short relaxation steps, one barrier each.  (With the cost
+    // inside every step the CTA advanced one ~1400-cycle dependent chain per barrier: ncu barrier stall 4.3
+    // cycles per issue, FP64 pipe 36 %.)
+    constexpr int G = 4;
+    for (int k0 = 0; k0 < nsteps; k0 += G) {
+      double cst[G];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { const double z = __dsub_rn(xreg[q], yr[q]); r8[q] = __dmul_rn(z, z); }
+      for (int g = 0; g < G; ++g) cst[g] = 0.0;
+      // warp-uniform test: does any lane own a cell in this round?  If so every lane evaluates G costs
+      // branch-free (column clamped into range, results of cells it does not own are ignored) so that the
+      // compiler interleaves the G independent dependency chains.
+      const bool mine = row_ok && (k0 + G - 1 - tid >= 0) && (k0 - tid < Ty);
+      if (__any_sync(0xffffffffu, mine)) {
 #pragma unroll
-        for (int bk = 1; bk < NB8; ++bk) {
+        for (int g = 0; g < G; ++g) {
+          const int jc = min(max(k0 + g - tid, 0), Ty - 1);
+          const double* yr = Ys + (size_t)jc * DP;
+          double r8[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const double z = __dsub_rn(xreg[bk * 8 + q], yr[bk * 8 + q]);
-            r8[q] = __dadd_rn(r8[q], __dmul_rn(z, z));
+          for (int q = 0; q < 8; ++q) { const double z = __dsub_rn(xreg[q], yr[q]); r8[q] = __dmul_rn(z, z); }
+#pragma unroll
+          for (int bk = 1; bk < NB8; ++bk) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const double z = __dsub_rn(xreg[bk * 8 + q], yr[bk * 8 + q]);
+              r8[q] = __dadd_rn(r8[q], __dmul_rn(z, z));
+            }
           }
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r8[0], r8[1]), __dadd_rn(r8[2], r8[3])),
-                               __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
+          double res = __dadd_rn(__dadd_rn(__dadd_rn(r8[0], r8[1]), __dadd_rn(r8[2], r8[3])),
+                                 __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
 #pragma unroll
-        for (int e = 0; e < 7; ++e)
-          if (e < ntail) { const double z = __dsub_rn(xreg[NB8 * 8 + e], yr[NB8 * 8 + e]); res = __dadd_rn(res, __dmul_rn(z, z)); }
-        const double rt = sqrt(res);
-        const double dt = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
-        // predecessors: D[i-1][j] (up), D[i][j-1] (left), D[i-1][j-1] (diagonal)
-        double dup, ddg;
-        if (tid > 0) {
-          dup = Dk[((k + 2) % 3) * R + tid - 1];
-          ddg = (j > 0) ? Dk[((k + 1) % 3) * R + tid - 1] : CUDART_INF;
-        } else if (s > 0) {
-          dup = Dlp[j];
-          ddg = (j > 0) ? Dlp[j - 1] : CUDART_INF;
-        } else {
-          dup = CUDART_INF;
-          ddg = (j == 0) ? 0.0 : CUDART_INF;
+          for (int e = 0; e < 7; ++e)
+            if (e < ntail) { const double z = __dsub_rn(xreg[NB8 * 8 + e], yr[NB8 * 8 + e]); res = __dadd_rn(res, __dmul_rn(z, z)); }
+          const double rt = sqrt(res);
+          cst[g] = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
         }
-        const double up = dup + dt;
-        const double left = ((j > 0) ? myD : CUDART_INF) + dt;
-        const double diag = ddg + dt;
-        double best = up;
-        uint32_t dir = 0;
-        if (left < best) { best = left; dir = 1; }
-        if (diag < best) { best = diag; dir = 2; }
-        myD = best;
-        Dk[(k % 3) * R + tid] = best;
-        if (tid == rows - 1) Dlc[j] = best;
-        bpw |= dir << (2 * (j & 15));
-        if ((j & 15) == 15 || j == Ty - 1) { bprow[j >> 4] = bpw; bpw = 0; }
-        if (i == Tx - 1 && j == Ty - 1) p.dist[pair] = best;
       }
-      __syncthreads();
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int k = k0 + g;
+        if (k < nsteps) {  // uniform over the CTA
+          const int j = k - tid;
+          if (row_ok && j >= 0 && j < Ty) {
+            const double dt = cst[g];
+            // predecessors: D[i-1][j] (up), D[i][j-1] (left), D[i-1][j-1] (diagonal)
+            double dup, ddg;
+            if (tid > 0) {
+              dup = Dk[((k + 2) % 3) * R + tid - 1];
+              ddg = (j > 0) ? Dk[((k + 1) % 3) * R + tid - 1] : CUDART_INF;
+            } else if (s > 0) {
+              dup = Dlp[j];
+              ddg = (j > 0) ? Dlp[j - 1] : CUDART_INF;
+            } else {
+              dup = CUDART_INF;
+              ddg = (j == 0) ? 0.0 : CUDART_INF;
+            }
+            const double up = dup + dt;
+            const double left = ((j > 0) ? myD : CUDART_INF) + dt;
+            const double diag = ddg + dt;
+            double best = up;
+            uint32_t dir = 0;
+            if (left < best) { best = left; dir = 1; }
+            if (diag < best) { best = diag; dir = 2; }
+            myD = best;
+            Dk[(k % 3) * R + tid] = best;
+            if (tid == rows - 1) Dlc[j] = best;
+            bpw |= dir << (2 * (j & 15));
+            if ((j & 15) == 15 || j == Ty - 1) { bprow[j >> 4] = bpw; bpw = 0; }
+            if (i == Tx - 1 && j == Ty - 1) p.dist[pair] = best;
+          }
+          __syncthreads();
+        }
+      }
     }
   }
   // ---- back-track (warp 0) ----

@@ -90,14 +90,13 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   double* pb = reinterpret_cast<double*>(smem + g.off_pb);          // [ND][TT][NR][32]
 
   const int lane = threadIdx.x & 31;
-  // 0..NA-1 = assemblers, NA = solver.  The hardware deals the warps of a CTA round-robin to the four
-  // SM sub-partitions; with a fixed role per warp index every solver (latency bound, few instructions)
-  // would share one scheduler and the issue-hungry assemblers the other three.  Rotating the roles by
-  // the CTA index gives every scheduler the same mix.
-#ifdef NNK_AS_NO_ROTATE
-  const int role = threadIdx.x >> 5;
-#else
+  // 0..NA-1 = assemblers, NA = solver.  (Rotating the roles by the CTA index so that every SM sub-partition
+  // hosts the same mix of assembler and solver warps was measured and is slower: configs[1] 0.148 -> 0.151 ms,
+  // gradient 0.231 -> 0.254 ms; -DNNK_AS_ROTATE keeps the experiment buildable.)
+#ifdef NNK_AS_ROTATE
   const int role = (int)(((threadIdx.x >> 5) + blockIdx.x) % (NA + 1));
+#else
+  const int role = threadIdx.x >> 5;
 #endif
   const int item = blockIdx.x;
   const int urank = p.urank0 + item / p.n_groups;

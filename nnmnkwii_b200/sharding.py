@@ -136,7 +136,11 @@ class PeerTransport(object):
                 self.peer_ptr[r] = out.value
             self.block = _DeviceBlock(self.local_ptr, (max(1, rows), cols), "<f4" if dtype == torch.float32 else "<f8")
             self.tensor = torch.as_tensor(self.block, device=device)
-            self.streams = [torch.cuda.Stream(device=device) if r != self.rank else None for r in range(self.world)]
+            # one copy engine moves ~0.5 TB/s of NVLink's 0.9: with few peers every push is split over several
+            # streams (= engines); with seven peers the seven streams already run in parallel
+            self.split = max(1, 4 // max(1, self.world - 1))
+            self.streams = [[torch.cuda.Stream(device=device) for _ in range(self.split)] if r != self.rank else None
+                            for r in range(self.world)]
             self.flag = torch.zeros(1, dtype=torch.int32, device=device)
         dist.barrier(group=group)
 
@@ -144,20 +148,26 @@ class PeerTransport(object):
         """Copy rows [row0, row0 + n_rows) of the local block into the same rows of every peer's block
         (copy engines, one stream per peer), once ``after_event`` (recorded behind the solve) has fired."""
         from . import _lib
-        off, nbytes = row0 * self.row_bytes, n_rows * self.row_bytes
+        if n_rows == 0:
+            return
+        per = -(-n_rows // self.split)
         for r in range(self.world):
-            if r == self.rank or nbytes == 0:
+            if r == self.rank:
                 continue
-            st = self.streams[r]
-            st.wait_event(after_event)
-            _lib.check(_lib.lib.nnk_peer_copy(ctypes.c_void_p(self.peer_ptr[r] + off), ctypes.c_void_p(self.local_ptr + off),
-                                              ctypes.c_size_t(nbytes), ctypes.c_void_p(st.cuda_stream)), "nnk_peer_copy")
+            for c, st in enumerate(self.streams[r]):
+                a, e = min(n_rows, c * per), min(n_rows, (c + 1) * per)
+                if e <= a:
+                    continue
+                off, nbytes = (row0 + a) * self.row_bytes, (e - a) * self.row_bytes
+                st.wait_event(after_event)
+                _lib.check(_lib.lib.nnk_peer_copy(ctypes.c_void_p(self.peer_ptr[r] + off), ctypes.c_void_p(self.local_ptr + off),
+                                                  ctypes.c_size_t(nbytes), ctypes.c_void_p(st.cuda_stream)), "nnk_peer_copy")
 
     def finish(self, stream):
         """``stream`` waits for this rank's pushes, then for every other rank's (tiny NCCL all-reduce)."""
         import torch.distributed as dist
-        for st in self.streams:
-            if st is not None:
+        for sts in self.streams:
+            for st in (sts or ()):
                 stream.wait_stream(st)
         dist.all_reduce(self.flag, group=self.group)
 
