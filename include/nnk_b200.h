@@ -240,6 +240,30 @@ int nnk_f0_metric(const void* src_f0, const void* src_vuv, const void* tgt_f0, c
                   int32_t kind, double* sum_out, int64_t* count_out, void* workspace, int64_t workspace_bytes,
                   void* stream);
 
+/* ---- GMM mapping in front of MLPG (baseline/gmm.py:47-247) ---------------------
+ * Device tables of a joint source/target GMM with M mixtures over D-dimensional frames, float64:
+ *   src_means, tgt_means (M, D); prec_chol (M, D, D) = sklearn precisions_cholesky_ of the source marginal
+ *   (U_m, row-major [d][e]); log_const (M) = log w_m + log det U_m - D/2 log 2pi;
+ *   A_t (M, D, D) = (Syx_m Sxx_m^-1)^T, row-major [j][i]; Dm (M, D) = Eq. 23 diagonal variances (may be
+ *   NULL when no variances are requested).
+ * nnk_gmm_logprob: lp (T, M) = log w_m + log N(x_t | mu_m, Sxx_m)  -- the per-frame predict_proba /
+ *   posterior of gmm.py:116-118, 219-221 before normalisation.
+ * nnk_gmm_map: mode 0 = MLPG.transform's arg-max mixture sequence (gmm.py:219-237): E[t] = Eq. 22 mean,
+ *   Dv[t] = Eq. 23 variance of the chosen mixture, mix[t] = its index (Dv / mix may be NULL);
+ *   mode 1 = MLPGBase._transform_frame (gmm.py:97-121): E[t] = posterior-weighted mean, Eq. 13.     */
+typedef struct nnk_gmm {
+  const double* src_means;
+  const double* tgt_means;
+  const double* prec_chol;
+  const double* log_const;
+  const double* A_t;
+  const double* Dm;
+  int32_t M, D;
+} nnk_gmm_t;
+int nnk_gmm_logprob(const nnk_gmm_t* gmm, const double* x, int64_t x_ld, int32_t T, double* lp, void* stream);
+int nnk_gmm_map(const nnk_gmm_t* gmm, const double* x, int64_t x_ld, int32_t T, const double* lp, int32_t mode, double* E,
+                double* Dv, int32_t* mix, void* stream);
+
 /* ---- sharded batches (the reference has no multi-device path) ------------------------
  * Copies n_seg row segments (whole utterances) between two row-major device matrices:
  * dst[dst_row[s] + r, 0:cols] = src[src_row[s] + r, 0:cols] for r < len[s].  Used to bring the

@@ -58,6 +58,14 @@ class NnkMlpgArgs(ctypes.Structure):
     ]
 
 
+class NnkGmm(ctypes.Structure):
+    _fields_ = [
+        ("src_means", ctypes.c_void_p), ("tgt_means", ctypes.c_void_p), ("prec_chol", ctypes.c_void_p),
+        ("log_const", ctypes.c_void_p), ("A_t", ctypes.c_void_p), ("Dm", ctypes.c_void_p),
+        ("M", ctypes.c_int32), ("D", ctypes.c_int32),
+    ]
+
+
 class NnkDtwArgs(ctypes.Structure):
     _fields_ = [
         ("X", ctypes.c_void_p),
@@ -95,7 +103,7 @@ EXPORTS = [
     "nnk_mlpg_fwd", "nnk_mlpg_grad", "nnk_mlpg_solve", "nnk_mlpg_workspace_bytes", "nnk_mlpg_host", "nnk_mlpg_batch_host",
     "nnk_uv_band_profile", "nnk_uv_band_extract", "nnk_uv_apply", "nnk_uv_apply_toeplitz", "nnk_uv_apply_factored",
     "nnk_dtw_align", "nnk_dtw_workspace_bytes", "nnk_gather_rows", "nnk_trim_lengths", "nnk_delta_features",
-    "nnk_metric_workspace_bytes", "nnk_frame_metric", "nnk_f0_metric", "nnk_segment_copy",
+    "nnk_metric_workspace_bytes", "nnk_frame_metric", "nnk_f0_metric", "nnk_segment_copy", "nnk_gmm_logprob", "nnk_gmm_map",
     "nnk_peer_alloc", "nnk_peer_free", "nnk_peer_export", "nnk_peer_open", "nnk_peer_close", "nnk_peer_copy",
 ]
 
@@ -162,6 +170,10 @@ def _load():
                        ("nnk_peer_copy", [vp, vp, ctypes.c_size_t, vp])):
         getattr(L, name).restype = ctypes.c_int
         getattr(L, name).argtypes = args
+    L.nnk_gmm_logprob.restype = ctypes.c_int
+    L.nnk_gmm_logprob.argtypes = [ctypes.POINTER(NnkGmm), vp, i64, i32, vp, vp]
+    L.nnk_gmm_map.restype = ctypes.c_int
+    L.nnk_gmm_map.argtypes = [ctypes.POINTER(NnkGmm), vp, i64, i32, vp, i32, vp, vp, vp, vp]
     L.nnk_segment_copy.restype = ctypes.c_int
     L.nnk_segment_copy.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, vp, i32, i32, vp]
     return L

@@ -7,10 +7,13 @@ frame); here the mixture posteriors, the per-frame affine maps and the variances
 whole utterance -- or a whole batch of utterances -- on the GPU in float64 and handed to the MLPG
 kernels without leaving the device.
 
-The per-mixture matrices ``A[m] = covarYX[m] covarXX[m]^-1`` are formed once in ``__init__`` (the
-reference re-solves per frame, gmm.py:113-115, 231-233); the dense (frames x mixtures x dim) algebra
-uses torch (cuBLAS) -- it is glue in front of the hot path, the banded solves are libnnk_b200's.
+The per-mixture matrices ``A[m] = covarYX[m] covarXX[m]^-1`` are formed once (the reference re-solves
+per frame, gmm.py:113-115, 231-233).  Posteriors, arg-max mixture, affine map and variances run in the
+float64 kernels of csrc/nnk_gmm.cu (C ABI ``nnk_gmm_logprob`` / ``nnk_gmm_map``): no (frames, mixtures,
+dim) temporaries, ``E`` and ``D`` are written directly in the layout the MLPG kernels read.
 """
+import ctypes
+
 import numpy as np
 from scipy import linalg
 
@@ -77,33 +80,51 @@ class MLPGBase(object):
         # Eq. (23) with diagonal covariances (gmm.py:239-244)
         Dm = np.stack([np.diag(self.covarYY[m]) - np.diag(self.covarYX[m]) / np.diag(self.covarXX[m]) * np.diag(self.covarXY[m])
                        for m in range(self.num_mixtures)])
-        self._dev = {
-            "device": device, "src_means": t(self.src_means), "tgt_means": t(self.tgt_means), "A": t(A),
-            "prec_chol": t(self._prec_chol), "Dm": t(Dm),
+        from .. import _lib
+        tabs = {
+            "src_means": t(self.src_means), "tgt_means": t(self.tgt_means), "prec_chol": t(self._prec_chol),
             "log_const": t(log_det + np.log(self.weights) - 0.5 * dim * np.log(2.0 * np.pi)),
+            "A_t": t(A.transpose(0, 2, 1)), "Dm": t(Dm),
         }
+        g = _lib.NnkGmm()
+        for k, v in tabs.items():
+            setattr(g, k, v.data_ptr())
+        g.M, g.D = self.num_mixtures, dim
+        self._dev = {"device": device, "tabs": tabs, "gmm": g}
         return self._dev
-
-    def _weighted_log_prob(self, x, c):
-        """log w_m + log N(x_t | mu_m, Sigma_xx,m) for every frame and mixture, (T, M)."""
-        import torch
-        diff = x[:, None, :] - c["src_means"][None]                       # (T, M, D)
-        y = torch.einsum("tmd,mde->tme", diff, c["prec_chol"])           # (x - mu) U
-        return c["log_const"][None, :] - 0.5 * (y * y).sum(-1)
-
-    def _frame_means(self, x, c, mix=None):
-        """Eq. (11)/(22): tgt_mean_m + A_m (x_t - src_mean_m); all mixtures (T, M, D) or the chosen one (T, D)."""
-        import torch
-        if mix is None:
-            diff = x[:, None, :] - c["src_means"][None]
-            return c["tgt_means"][None] + torch.einsum("mij,tmj->tmi", c["A"], diff)
-        diff = x - c["src_means"][mix]
-        return c["tgt_means"][mix] + torch.bmm(c["A"][mix], diff[:, :, None])[:, :, 0]
 
     def _to_device(self, src):
         import torch
         c = self._constants()
         return torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64)).to(c["device"]), c
+
+    def _weighted_log_prob(self, x, c):
+        """log w_m + log N(x_t | mu_m, Sigma_xx,m) for every frame and mixture, (T, M) (Eq. 9 before
+        normalisation; the reference: sklearn predict_proba per frame, gmm.py:116-118)."""
+        import torch
+
+        from .. import _device as dev
+        from .. import _lib
+        T = x.shape[0]
+        lp = torch.empty((T, self.num_mixtures), dtype=torch.float64, device=x.device)
+        _lib.check(_lib.lib.nnk_gmm_logprob(ctypes.byref(c["gmm"]), x.data_ptr(), x.stride(0), T, lp.data_ptr(),
+                                            dev.current_stream_ptr(x.device)), "nnk_gmm_logprob")
+        return lp
+
+    def _map(self, x, c, mode, want_var=False):
+        """mode 0: (E, D, mix) of the arg-max mixture sequence (Eq. 37, 22, 23); mode 1: posterior mean (Eq. 13)."""
+        import torch
+
+        from .. import _device as dev
+        from .. import _lib
+        T, D = x.shape
+        lp = self._weighted_log_prob(x, c)
+        E = torch.empty((T, D), dtype=torch.float64, device=x.device)
+        Dv = torch.empty((T, D), dtype=torch.float64, device=x.device) if want_var else None
+        _lib.check(_lib.lib.nnk_gmm_map(ctypes.byref(c["gmm"]), x.data_ptr(), x.stride(0), T, lp.data_ptr(), mode, E.data_ptr(),
+                                        Dv.data_ptr() if want_var else None, None, dev.current_stream_ptr(x.device)),
+                   "nnk_gmm_map")
+        return E, Dv
 
     def transform(self, src):
         src = np.asarray(src)
@@ -118,16 +139,12 @@ class MLPGBase(object):
         """``E[p(y | x)]`` of one frame (gmm.py:97-121)."""
         return self._transform_frames(np.asarray(src)[None])[0]
 
-    def _transform_frames(self, src, chunk=1 << 16):
-        import torch
+    def _transform_frames(self, src):
         xa, c = self._to_device(src)
-        out = torch.empty_like(xa)
-        for a in range(0, xa.shape[0], chunk):  # bounds the (frames, mixtures, dim) temporaries
-            x = xa[a:a + chunk]
-            post = torch.softmax(self._weighted_log_prob(x, c), dim=1)   # Eq. (9)
-            E = self._frame_means(x, c)                                   # Eq. (11)
-            out[a:a + chunk] = torch.einsum("tm,tmi->ti", post, E)        # Eq. (13)
-        return out.cpu().numpy()
+        if xa.shape[0] == 0:
+            return xa.cpu().numpy()
+        E, _ = self._map(xa.contiguous(), c, 1)  # Eq. (9), (11), (13) in one pass per frame tile
+        return E.cpu().numpy()
 
 
 class MLPG(MLPGBase):
@@ -149,8 +166,7 @@ class MLPG(MLPGBase):
 
     def _means_vars(self, x, c):
         """E (Eq. 22) and D (Eq. 23) of the sub-optimum mixture sequence (Eq. 37), on the device."""
-        mix = self._weighted_log_prob(x, c).argmax(dim=1)
-        return self._frame_means(x, c, mix), c["Dm"][mix]
+        return self._map(x.contiguous(), c, 0, want_var=True)
 
     def transform(self, src):
         """Source feature sequence ``(T, D)`` -> converted static features ``(T, static_dim)``."""

@@ -723,22 +723,32 @@ __global__ void __launch_bounds__(256) dtw_dp_kernel(const DtwExactParams p) {
 }
 
 // ---- exact DTW, fused (the production path for frames of 8..39 dims that fit shared memory) -----------------
-// One CTA per pair, one wavefront: the local cost of a cell is computed in registers at the moment the
+// One CTA (16 warps) per pair; the local cost of a cell is computed in registers at the moment the
 // recurrence needs it -- there is NO Tx x Ty cost matrix in HBM (the two-kernel path above wrote and
 // re-read 8 bytes per cell: 5 GB per configs[3] batch against 0.25 GB of algorithmic traffic).
 //   * all of Y (float64, conflict-free row stride) is staged ONCE in shared memory;
-//   * the rows of X are processed in strips of R = 512: thread r of a strip owns row i = strip*R + r and
-//     keeps its frame of X in registers (float64) for the whole strip;
-//   * step k of a strip relaxes the cells (r, j = k - r): cost from registers x shared-memory Y in
-//     numpy's pairwise order (bit-exact, no FMA contraction), predecessors from the thread's own
-//     register (left), from the neighbouring thread through three rolling shared-memory diagonals (up,
-//     diagonal), or -- for the first row of a strip -- from the last row of the previous strip kept in
-//     shared memory; one __syncthreads per step;
-//   * back-pointers are 2 bits per cell, packed by the owning thread into one 32-bit word per 16
-//     columns, row-major in an L2-resident scratch (40 KB.. 200 KB per pair instead of 1 byte per cell);
+//   * the rows of X are cut into groups of 32; warp w owns groups w, w + 16, ...  Lane l of the warp owns
+//     row i = 32 g + l, keeps its frame of X in registers (float64) and walks the columns: at step s it
+//     relaxes cell (i, j = s - l) -- the warp is one 32-cell anti-diagonal wavefront that streams over all
+//     Ty columns with every lane busy.  Predecessors: left = the lane's own register, up / diagonal = the
+//     neighbouring lane's register by shuffle; lane 0 takes them from the last row of the previous group;
+//   * groups are a software pipeline, not lock-stepped: lane 31 publishes its row into a small ring in
+//     shared memory (DTW_CW columns per boundary) together with a progress counter, the warp that owns
+//     the next group polls it every DTW_POLL steps (and publishes how far it has read, so the producer
+//     never overwrites unread columns).  No __syncthreads inside the recurrence: a first version that
+//     advanced one diagonal of 512 rows per barrier left half of the warps idle (the triangle ramps) and
+//     spent 4.1 stall cycles per issue at the barrier (profiles/r02_dtw_fused_v1_barrier_ncu.txt);
+//   * cost: numpy's pairwise order, float64, no FMA contraction (bit-exact), two columns per loop trip so
+//     that the sqrt chain of one cell overlaps the element-wise work of the next;
+//   * back-pointers are 2 bits per cell, packed by the owning lane into one 32-bit word per 16 columns,
+//     row-major in an L2-resident scratch (200 KB per pair instead of 1 byte per cell);
 //   * the back-track is a pointer chase: warp 0 loads a 32-row x 32-column window of back-pointer words
 //     with one coalesced round trip, walks it by shuffles, and reloads when the path leaves the window.
 constexpr int DTW_FR = 512;
+constexpr int DTW_NWARP = DTW_FR / 32;
+constexpr int DTW_CW = 128;    // columns per boundary ring
+constexpr int DTW_NBR = DTW_NWARP + 1;  // boundary rings (one per group in flight + the one being read)
+constexpr int DTW_POLL = 8;    // steps between progress checks / publications
 
 struct DtwFusedParams {
   const void* X;
@@ -763,7 +773,6 @@ struct DtwFusedParams {
 
 template <typename T, int NB8>
 __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedParams p) {
-  constexpr int R = DTW_FR;
   extern __shared__ __align__(16) unsigned char smem_f[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = blockIdx.x;
@@ -774,109 +783,119 @@ __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedPara
     return;
   }
   const int D = p.D, DP = dtw_row_stride(D);
-  double* Ys = reinterpret_cast<double*>(smem_f);          // [max_ty][DP]
-  double* Dk = Ys + (size_t)p.max_ty * DP;                 // [3][R] rolling diagonals of the strip
-  double* Dl = Dk + 3 * R;                                 // [2][max_ty] last row of the previous / current strip
+  const int max_groups = (p.max_tx + 31) / 32;
+  double* Ys = reinterpret_cast<double*>(smem_f);              // [max_ty][DP]
+  double* Bnd = Ys + (size_t)p.max_ty * DP;                    // [DTW_NBR][DTW_CW] last rows of the groups in flight
+  volatile int* prog = reinterpret_cast<volatile int*>(Bnd + DTW_NBR * DTW_CW);  // [groups] columns published by group g
+  volatile int* cons = prog + max_groups + 1;                                   // [groups] columns group g has read
   const T* X = reinterpret_cast<const T*>(p.X) + (int64_t)pair * p.x_pair_stride;
   const T* Y = reinterpret_cast<const T*>(p.Y) + (int64_t)pair * p.y_pair_stride;
-  for (int e = tid; e < Ty * D; e += R) {
+  for (int e = tid; e < Ty * D; e += DTW_FR) {
     const int r = e / D, k = e - r * D;
     Ys[(size_t)r * DP + k] = (double)Y[(int64_t)r * p.y_ld + k];
   }
+  for (int e = tid; e < 2 * (max_groups + 1); e += DTW_FR) prog[e] = 0;
+  __syncthreads();
   uint32_t* bp = p.bp + (size_t)slot * ((size_t)p.max_tx * p.wpr);
   const int ntail = D - NB8 * 8;
-  const int nstrip = (Tx + R - 1) / R;
-  for (int s = 0; s < nstrip; ++s) {
-    const int i = s * R + tid;
+  const int ngroups = (Tx + 31) / 32;
+  const int nsteps = Ty + 31;
+  for (int g = warp; g < ngroups; g += DTW_NWARP) {
+    const int i = g * 32 + lane;
     const bool row_ok = i < Tx;
-    const int rows = min(R, Tx - s * R);
     double xreg[NB8 * 8 + 8];
 #pragma unroll
     for (int e = 0; e < NB8 * 8 + 8; ++e) xreg[e] = (row_ok && e < D) ? (double)X[(int64_t)i * p.x_ld + e] : 0.0;
-    const double* Dlp = Dl + (size_t)(s & 1) * p.max_ty;        // written by strip s - 1
-    double* Dlc = Dl + (size_t)((s + 1) & 1) * p.max_ty;        // written by this strip
-    double myD = 0.0;
+    const double* bprev = Bnd + (size_t)((g + DTW_NBR - 1) % DTW_NBR) * DTW_CW;  // written by group g - 1
+    double* bcur = Bnd + (size_t)(g % DTW_NBR) * DTW_CW;                          // read by group g + 1
+    const bool feeds = (g + 1 < ngroups);
+    double myD = CUDART_INF;     // D[i][j-1] of the lane's current column (left)
+    double uprev = CUDART_INF;   // D[i-1][j-1] (diagonal) = what the neighbour held one step earlier
     uint32_t bpw = 0;
     uint32_t* bprow = bp + (size_t)i * p.wpr;
-    __syncthreads();  // Ys staged (s == 0) / previous strip's last row complete
-    const int nsteps = rows + Ty - 1;
-    // Rounds of G steps: (A) the local costs of the thread's next G cells -- independent of the recurrence,
-    // G cells in flight per thread so that the long sqrt / reduction chains of one cell overlap the
-    // element-wise work of the next -- then (B) G short relaxation steps, one barrier each.  (With the cost
-    // inside every step the CTA advanced one ~1400-cycle dependent chain per barrier: ncu barrier stall 4.3
-    // cycles per issue, FP64 pipe 36 %.)
-    constexpr int G = 4;
-    for (int k0 = 0; k0 < nsteps; k0 += G) {
-      double cst[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) cst[g] = 0.0;
-      // warp-uniform test: does any lane own a cell in this round?  If so every lane evaluates G costs
-      // branch-free (column clamped into range, results of cells it does not own are ignored) so that the
-      // compiler interleaves the G independent dependency chains.
-      const bool mine = row_ok && (k0 + G - 1 - tid >= 0) && (k0 - tid < Ty);
-      if (__any_sync(0xffffffffu, mine)) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int jc = min(max(k0 + g - tid, 0), Ty - 1);
-          const double* yr = Ys + (size_t)jc * DP;
-          double r8[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) { const double z = __dsub_rn(xreg[q], yr[q]); r8[q] = __dmul_rn(z, z); }
-#pragma unroll
-          for (int bk = 1; bk < NB8; ++bk) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const double z = __dsub_rn(xreg[bk * 8 + q], yr[bk * 8 + q]);
-              r8[q] = __dadd_rn(r8[q], __dmul_rn(z, z));
-            }
-          }
-          double res = __dadd_rn(__dadd_rn(__dadd_rn(r8[0], r8[1]), __dadd_rn(r8[2], r8[3])),
-                                 __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
-#pragma unroll
-          for (int e = 0; e < 7; ++e)
-            if (e < ntail) { const double z = __dsub_rn(xreg[NB8 * 8 + e], yr[NB8 * 8 + e]); res = __dadd_rn(res, __dmul_rn(z, z)); }
-          const double rt = sqrt(res);
-          cst[g] = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
+    for (int s0 = 0; s0 < nsteps; s0 += 2) {
+      if ((s0 & (DTW_POLL - 1)) == 0) {
+        // (1) publish: lane 0 has consumed boundary columns < s0; lane 31 has produced columns <= s0 - 32
+        __syncwarp();
+        if (lane == 0 && g > 0) cons[g] = s0;
+        if (lane == 31 && feeds) { __threadfence_block(); prog[g] = max(0, s0 - 31); }
+        // (2) wait: the previous group must have published the columns lane 0 reads in the next DTW_POLL
+        //     steps; the next group must have read the ring slots lane 31 is about to overwrite
+        if (g > 0) {
+          const int need = min(Ty, s0 + DTW_POLL);
+          while (prog[g - 1] < need) __nanosleep(40);
         }
+        if (feeds) {
+          const int j_hi = s0 + DTW_POLL - 1 - 31;  // last column lane 31 writes before the next check
+          while (j_hi - DTW_CW + 2 > cons[g + 1]) __nanosleep(40);
+        }
+        __threadfence_block();
+        __syncwarp();
       }
+      // ---- local costs of this lane's cells of steps s0, s0 + 1 (branch-free, columns clamped) ----
+      double cst[2];
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int k = k0 + g;
-        if (k < nsteps) {  // uniform over the CTA
-          const int j = k - tid;
-          if (row_ok && j >= 0 && j < Ty) {
-            const double dt = cst[g];
-            // predecessors: D[i-1][j] (up), D[i][j-1] (left), D[i-1][j-1] (diagonal)
-            double dup, ddg;
-            if (tid > 0) {
-              dup = Dk[((k + 2) % 3) * R + tid - 1];
-              ddg = (j > 0) ? Dk[((k + 1) % 3) * R + tid - 1] : CUDART_INF;
-            } else if (s > 0) {
-              dup = Dlp[j];
-              ddg = (j > 0) ? Dlp[j - 1] : CUDART_INF;
-            } else {
-              dup = CUDART_INF;
-              ddg = (j == 0) ? 0.0 : CUDART_INF;
-            }
-            const double up = dup + dt;
-            const double left = ((j > 0) ? myD : CUDART_INF) + dt;
-            const double diag = ddg + dt;
-            double best = up;
-            uint32_t dir = 0;
-            if (left < best) { best = left; dir = 1; }
-            if (diag < best) { best = diag; dir = 2; }
-            myD = best;
-            Dk[(k % 3) * R + tid] = best;
-            if (tid == rows - 1) Dlc[j] = best;
-            bpw |= dir << (2 * (j & 15));
-            if ((j & 15) == 15 || j == Ty - 1) { bprow[j >> 4] = bpw; bpw = 0; }
-            if (i == Tx - 1 && j == Ty - 1) p.dist[pair] = best;
+      for (int q = 0; q < 2; ++q) {
+        const int jc = min(max(s0 + q - lane, 0), Ty - 1);
+        const double* yr = Ys + (size_t)jc * DP;
+        double r8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const double z = __dsub_rn(xreg[e], yr[e]); r8[e] = __dmul_rn(z, z); }
+#pragma unroll
+        for (int bk = 1; bk < NB8; ++bk) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const double z = __dsub_rn(xreg[bk * 8 + e], yr[bk * 8 + e]);
+            r8[e] = __dadd_rn(r8[e], __dmul_rn(z, z));
           }
-          __syncthreads();
         }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r8[0], r8[1]), __dadd_rn(r8[2], r8[3])),
+                               __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
+#pragma unroll
+        for (int e = 0; e < 7; ++e)
+          if (e < ntail) { const double z = __dsub_rn(xreg[NB8 * 8 + e], yr[NB8 * 8 + e]); res = __dadd_rn(res, __dmul_rn(z, z)); }
+        const double rt = sqrt(res);
+        cst[q] = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
+      }
+      // ---- two relaxation steps ----
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int s = s0 + q;
+        const int j = s - lane;
+        // up = D[i-1][j]: the neighbouring lane finished that cell in the previous step
+        double u = __shfl_up_sync(0xffffffffu, myD, 1);
+        if (lane == 0) {
+          if (g > 0) {
+            u = (s < Ty) ? bprev[s & (DTW_CW - 1)] : CUDART_INF;
+            uprev = (s > 0 && s <= Ty) ? bprev[(s - 1) & (DTW_CW - 1)] : CUDART_INF;
+          } else {
+            u = CUDART_INF;
+            uprev = (s == 0) ? 0.0 : CUDART_INF;  // the virtual cell before (0, 0)
+          }
+        }
+        if (row_ok && j >= 0 && j < Ty) {
+          const double dt = cst[q];
+          const double up = u + dt;
+          const double left = myD + dt;     // myD == +inf before the lane's first column
+          const double diag = uprev + dt;
+          double best = up;
+          uint32_t dir = 0;
+          if (left < best) { best = left; dir = 1; }
+          if (diag < best) { best = diag; dir = 2; }
+          myD = best;
+          if (lane == 31 && feeds) bcur[j & (DTW_CW - 1)] = best;
+          bpw |= dir << (2 * (j & 15));
+          if ((j & 15) == 15 || j == Ty - 1) { bprow[j >> 4] = bpw; bpw = 0; }
+          if (i == Tx - 1 && j == Ty - 1) p.dist[pair] = best;
+        }
+        uprev = u;
       }
     }
+    if (lane == 31 && feeds) { __threadfence_block(); prog[g] = Ty; }
+    if (lane == 0 && g > 0) cons[g] = nsteps + DTW_CW;
+    __syncwarp();
   }
+  __syncthreads();
   // ---- back-track (warp 0) ----
   __shared__ int s_n;
   if (warp == 0) {
@@ -908,7 +927,7 @@ __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedPara
   if (n > 0) {
     int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
     int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
-    for (int a = tid; a < n / 2; a += R) {
+    for (int a = tid; a < n / 2; a += DTW_FR) {
       const int b = n - 1 - a;
       const int32_t ti = pi[a], tj = pj[a];
       pi[a] = pi[b]; pj[a] = pj[b];
@@ -921,14 +940,15 @@ __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedPara
   }
 }
 
-static size_t dtw_fused_smem(int max_ty, int D) {
+static size_t dtw_fused_smem(int max_tx, int max_ty, int D) {
   int dp = (D + 1) & ~1;
   if (((dp >> 1) & 1) == 0) dp += 2;
-  return sizeof(double) * ((size_t)max_ty * dp + 3 * DTW_FR + 2 * (size_t)max_ty) + 16;
+  const size_t groups = (size_t)(max_tx + 31) / 32;
+  return sizeof(double) * ((size_t)max_ty * dp + (size_t)DTW_NBR * DTW_CW) + sizeof(int) * 2 * (groups + 1) + 16;
 }
 // the fused kernel serves frames of 8..39 dimensions whose Y series fits shared memory as float64
-static bool dtw_fused_ok(int max_ty, int D, size_t max_smem) {
-  return D >= 8 && D < 40 && dtw_fused_smem(max_ty, D) <= max_smem;
+static bool dtw_fused_ok(int max_tx, int max_ty, int D, size_t max_smem) {
+  return D >= 8 && D < 40 && dtw_fused_smem(max_tx, max_ty, D) <= max_smem;
 }
 static bool dtw_force_two_pass() {
   static int v = -1;
@@ -1066,7 +1086,7 @@ extern "C" int nnk_dtw_align(const nnk_dtw_args_t* a, void* stream) {
   int dev = 0, max_smem = 0;
   NNK_CUDA_CHECK(cudaGetDevice(&dev));
   NNK_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if (full && !dtw_force_two_pass() && dtw_fused_ok(a->max_ty, a->D, (size_t)max_smem)) {
+  if (full && !dtw_force_two_pass() && dtw_fused_ok(a->max_tx, a->max_ty, a->D, (size_t)max_smem)) {
     DtwFusedParams f;
     f.X = a->X; f.Y = a->Y; f.x_pair_stride = a->x_pair_stride; f.y_pair_stride = a->y_pair_stride;
     f.x_ld = a->x_ld; f.y_ld = a->y_ld; f.D = a->D; f.len_x = a->len_x; f.len_y = a->len_y; f.order = a->order;
@@ -1075,7 +1095,7 @@ extern "C" int nnk_dtw_align(const nnk_dtw_args_t* a, void* stream) {
     f.bp = reinterpret_cast<uint32_t*>(a->workspace);
     f.wpr = (a->max_ty + 15) / 16;
     f.logdb = p.logdb;
-    const size_t fsmem = dtw_fused_smem(a->max_ty, a->D);
+    const size_t fsmem = dtw_fused_smem(a->max_tx, a->max_ty, a->D);
     const int nb8 = a->D / 8;
 #define NNK_FUSED(TT_, NB_)                                                                                         \
   do {                                                                                                              \

@@ -39,7 +39,7 @@ src = run("source")
 if len(src) > 2:
     h = src[1]
     ix = {k: i for i, k in enumerate(h)}
-    data = [r for r in src[2:] if len(r) == len(h)]
+    data = [r for r in src[2:] if len(r) == len(h) and r[ix["# Samples"]].strip().isdigit()]
     tot = sum(int(r[ix["# Samples"]]) for r in data)
 
     def op(r):
