@@ -68,7 +68,13 @@ def config(n_gpus):
 
 
 # ---- configs[4]: 8192 utterances, mixed T, strong scaling ---------------------------------------------
-CFG5_UTT, CFG5_T_LO, CFG5_T_HI, CFG5_BUCKETS = 8192, 200, 2000, 4
+CFG5_UTT, CFG5_T_LO, CFG5_T_HI = 8192, 200, 2000
+
+
+def cfg5_buckets(world):
+    """Buckets per pass: enough that the last (exposed) transfer is a small part of the pass, few enough
+    that a bucket still fills the GPU (>= 512 utterances = 1024 CTAs per launch): 8 / 8 / 4 / 2 at 1 / 2 / 4 / 8 ranks."""
+    return max(2, min(8, CFG5_UTT // world // 512))
 
 
 def cfg5_lengths():
@@ -91,10 +97,10 @@ def config_cfg5(n_gpus):
                     "longest-first greedy per bucket), inputs pre-sharded in HBM, per bucket solve -> in-place "
                     "all-gather (copy-engine pushes into IPC-shared peer buffers over NVLink; NNK_SHARD_TRANSPORT=nccl: NCCL "
                     "all_gather_into_tensor) overlapped with the next bucket; every rank ends with all trajectories"
-                    % (CFG5_UTT, CFG5_T_LO, CFG5_T_HI, n_gpus, CFG5_BUCKETS),
-        "utterances": CFG5_UTT, "static_dims": 62, "windows": 3, "buckets": CFG5_BUCKETS,
+                    % (CFG5_UTT, CFG5_T_LO, CFG5_T_HI, n_gpus, cfg5_buckets(n_gpus)),
+        "utterances": CFG5_UTT, "static_dims": 62, "windows": 3, "buckets": cfg5_buckets(n_gpus),
         "sharding": "utterance-sharded, %d rank(s), %d bucketed all-gathers per pass (the path's only collective)"
-                    % (n_gpus, CFG5_BUCKETS),
+                    % (n_gpus, cfg5_buckets(n_gpus)),
         "cache": "per-rank inputs (>= 1.7 GB) and factor scratch exceed the 126 MB L2; no explicit flush",
     }
 
@@ -316,7 +322,7 @@ class Cfg5Pass(object):
         self.rank, self.world, self.device = rank, world, device
         self.lens = cfg5_lengths()
         self.layout = G.merlin_layout()
-        self.plan = sharding.ShardPlan(self.lens, world, CFG5_BUCKETS)
+        self.plan = sharding.ShardPlan(self.lens, world, cfg5_buckets(world))
         self.transport = transport if world > 1 else None
         self.batch = sharding.ShardedBatch(self.plan, rank, device, D_IN, D_OUT, torch.float32, transport=self.transport)
         for b in range(self.plan.n_buckets):  # inputs are generated straight into the rank's HBM slice
