@@ -748,7 +748,7 @@ constexpr int DTW_FR = 512;
 constexpr int DTW_NWARP = DTW_FR / 32;
 constexpr int DTW_CW = 128;    // columns per boundary ring
 constexpr int DTW_NBR = DTW_NWARP + 1;  // boundary rings (one per group in flight + the one being read)
-constexpr int DTW_POLL = 16;   // steps between progress checks / publications
+constexpr int DTW_POLL = 8;    // steps between progress checks / publications
 
 struct DtwFusedParams {
   const void* X;
@@ -813,34 +813,6 @@ __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedPara
     double uprev = CUDART_INF;   // D[i-1][j-1] (diagonal) = what the neighbour held one step earlier
     uint32_t bpw = 0;
     uint32_t* bprow = bp + (size_t)i * p.wpr;
-    // local costs of this lane's cells of steps sb, sb + 1 (branch-free, columns clamped into range)
-    auto eval_costs = [&](int sb, double (&out)[2]) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int jc = min(max(sb + q - lane, 0), Ty - 1);
-        const double* yr = Ys + (size_t)jc * DP;
-        double r8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { const double z = __dsub_rn(xreg[e], yr[e]); r8[e] = __dmul_rn(z, z); }
-#pragma unroll
-        for (int bk = 1; bk < NB8; ++bk) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const double z = __dsub_rn(xreg[bk * 8 + e], yr[bk * 8 + e]);
-            r8[e] = __dadd_rn(r8[e], __dmul_rn(z, z));
-          }
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r8[0], r8[1]), __dadd_rn(r8[2], r8[3])),
-                               __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
-#pragma unroll
-        for (int e = 0; e < 7; ++e)
-          if (e < ntail) { const double z = __dsub_rn(xreg[NB8 * 8 + e], yr[NB8 * 8 + e]); res = __dadd_rn(res, __dmul_rn(z, z)); }
-        const double rt = sqrt(res);
-        out[q] = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
-      }
-    };
-    double cnext[2];
-    eval_costs(0, cnext);
     for (int s0 = 0; s0 < nsteps; s0 += 2) {
       if ((s0 & (DTW_POLL - 1)) == 0) {
         // (1) publish: lane 0 has consumed boundary columns < s0; lane 31 has produced columns <= s0 - 32
@@ -860,12 +832,31 @@ __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedPara
         __threadfence_block();
         __syncwarp();
       }
-      // ---- software pipeline: the costs of the NEXT trip's two cells are evaluated here, next to the two
-      //      relaxation steps of THIS trip (which use the costs computed one trip earlier): the relaxation
-      //      is a short serial chain (shuffle, add, compare, select), the cost block has 16-fold parallelism;
-      //      issued together they hide each other's latencies ----
-      double cst[2] = {cnext[0], cnext[1]};
-      eval_costs(s0 + 2, cnext);
+      // ---- local costs of this lane's cells of steps s0, s0 + 1 (branch-free, columns clamped) ----
+      double cst[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int jc = min(max(s0 + q - lane, 0), Ty - 1);
+        const double* yr = Ys + (size_t)jc * DP;
+        double r8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const double z = __dsub_rn(xreg[e], yr[e]); r8[e] = __dmul_rn(z, z); }
+#pragma unroll
+        for (int bk = 1; bk < NB8; ++bk) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const double z = __dsub_rn(xreg[bk * 8 + e], yr[bk * 8 + e]);
+            r8[e] = __dadd_rn(r8[e], __dmul_rn(z, z));
+          }
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r8[0], r8[1]), __dadd_rn(r8[2], r8[3])),
+                               __dadd_rn(__dadd_rn(r8[4], r8[5]), __dadd_rn(r8[6], r8[7])));
+#pragma unroll
+        for (int e = 0; e < 7; ++e)
+          if (e < ntail) { const double z = __dsub_rn(xreg[NB8 * 8 + e], yr[NB8 * 8 + e]); res = __dadd_rn(res, __dmul_rn(z, z)); }
+        const double rt = sqrt(res);
+        cst[q] = p.cost_kind == 1 ? __dmul_rn(p.logdb, rt) : rt;
+      }
       // ---- two relaxation steps ----
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
