@@ -11,9 +11,14 @@ count, and every group is split over the ranks by a longest-first greedy rule.  
 result buffer (``cap[b]`` = largest per-rank frame count of the bucket, so the dead rows are at most
 one utterance per bucket and rank -- no per-utterance padding).  The MLPG kernel writes straight into
 that slot (``nnk_mlpg_args_t.out_off``) and the all-gather of bucket ``b`` moves the contiguous region
-``[goff[b] + r * cap[b], ...)`` of every rank ``r`` to every other rank.  Two transports:
+``[goff[b] + r * cap[b], ...)`` of every rank ``r`` to every other rank.  Three transports:
 
-* ``"peer"`` (default on GPUs): the result buffers are cudaMalloc allocations shared between the per-GPU
+* ``"p2p"`` (default on GPUs): the result buffers are cudaMalloc allocations shared between the per-GPU
+  processes by CUDA IPC and the solve kernel itself stores every trajectory value to its own buffer AND to
+  the same slot of every peer's buffer (``nnk_mlpg_args_t.peer_out``: SM-issued stores over NVLink, behind
+  the recurrence).  Compute and collective are ONE kernel: there is no second pass over the result and
+  nothing to overlap; the pass ends with one tiny NCCL all-reduce ("everything has landed everywhere").
+* ``"peer"``: the result buffers are cudaMalloc allocations shared between the per-GPU
   processes by CUDA IPC; as soon as bucket ``b`` is solved every rank PUSHES its slot into its peers'
   buffers with copy-engine DMA over NVLink (``nnk_peer_copy``, one side stream per peer).  No SMs are
   involved, so the transfer really overlaps the solve of bucket ``b + 1`` (an NCCL all-gather kernel has
@@ -196,7 +201,8 @@ class ShardedBatch(object):
         self.means = torch.zeros((max(1, plan.rows_local), D_in), dtype=dtype, device=device)
         self.variances = torch.ones((max(1, plan.rows_local), D_in), dtype=dtype, device=device)
         self.peer = None
-        if transport == "peer" and plan.world > 1:
+        self.fused = (transport == "p2p")
+        if transport in ("peer", "p2p") and plan.world > 1:
             self.peer = PeerTransport(plan.rows_total, D_out, dtype, device, group)
             self.result = self.peer.tensor
         else:
@@ -281,7 +287,8 @@ def _solve_bucket(batch, b, windows_c, chains, n_chain, status):
                  offsets=m["utt_off"], lengths=m["utt_len"], order=None, chains=chains, n_chain=n_chain,
                  max_T=m["max_T"], windows_c=windows_c, in_ld=batch.D_in, var_ld=0 if var1d else batch.D_in, go_ld=0,
                  out_ld=batch.D_out, dtype_code=dev.torch_dtype_code(batch.dtype), go_f64=0, n_utt=m["n_utt"],
-                 device=batch.device, check=False, out_offsets=m["out_off"], status=status)
+                 device=batch.device, check=False, out_offsets=m["out_off"], status=status,
+                 peers=[p for p in batch.peer.peer_ptr if p] if (batch.peer is not None and batch.fused) else None)
 
 
 def _gather_bucket(result, plan, b, rank, group):
@@ -326,6 +333,11 @@ def solve_sharded(batch, windows, layout, group=None, comm_stream=None, status=N
                 _gather_bucket(batch.result, plan, b, rank, group)
         return None
     cur = torch.cuda.current_stream(batch.device)
+    if batch.peer is not None and batch.fused:  # the solve kernels store into every peer's buffer themselves
+        for b in range(plan.n_buckets):
+            _solve_bucket(batch, b, wc, chains, layout.n_chain, status)
+        batch.peer.finish(cur)
+        return None
     if batch.peer is not None:  # copy-engine pushes over NVLink, overlapped with the next bucket's solve
         for b in range(plan.n_buckets):
             _solve_bucket(batch, b, wc, chains, layout.n_chain, status)
@@ -364,12 +376,14 @@ def _comm_stream(device):
 
 
 def default_transport(device):
-    """"peer" on CUDA devices unless NNK_SHARD_TRANSPORT=nccl; the collective of the process group otherwise."""
+    """"p2p" on CUDA devices unless NNK_SHARD_TRANSPORT says "peer" or "nccl"; the collective of the process
+    group otherwise."""
     import os
     import torch
     if torch.device(device).type != "cuda":
         return None
-    return "nccl" if os.environ.get("NNK_SHARD_TRANSPORT", "peer") == "nccl" else "peer"
+    t = os.environ.get("NNK_SHARD_TRANSPORT", "p2p")
+    return t if t in ("p2p", "peer", "nccl") else "p2p"
 
 
 def mlpg_batch_sharded(means, variances, windows, lengths, layout=None, group=None, device=None, n_buckets=4,
