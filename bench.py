@@ -95,9 +95,8 @@ def config_cfg5(n_gpus):
         "workload": "configs[4]: %d-utterance paramgen.mlpg batch, T~U{%d..%d} (9.0e6 frames), D=187 Merlin layout, 3 windows, "
                     "per-frame diagonal variances, float32 I/O, STRONG-scaled over %d GPU(s): ShardPlan (%d buckets, "
                     "longest-first greedy per bucket), inputs pre-sharded in HBM, per bucket solve -> in-place "
-                    "all-gather (default p2p: the solve kernel stores every trajectory into its own and every peer's "
-                    "IPC-shared result buffer over NVLink; NNK_SHARD_TRANSPORT=peer: copy-engine pushes, =nccl: NCCL "
-                    "all_gather_into_tensor, both overlapped with the next bucket); every rank ends with all trajectories"
+                    "all-gather (copy-engine pushes into IPC-shared peer buffers over NVLink; NNK_SHARD_TRANSPORT=nccl: NCCL "
+                    "all_gather_into_tensor) overlapped with the next bucket; every rank ends with all trajectories"
                     % (CFG5_UTT, CFG5_T_LO, CFG5_T_HI, n_gpus, cfg5_buckets(n_gpus)),
         "utterances": CFG5_UTT, "static_dims": 62, "windows": 3, "buckets": cfg5_buckets(n_gpus),
         "sharding": "utterance-sharded, %d rank(s), %d bucketed all-gathers per pass (the path's only collective)"
@@ -346,16 +345,11 @@ class Cfg5Pass(object):
         from nnmnkwii_b200 import sharding
         wc = _lib.make_windows(WINDOWS)
         chains = dev.chains_on_device(self.layout.chains, self.device)
-        fused, self.batch.fused = self.batch.fused, False  # the solves alone: no mirroring to the peers
-        try:
-            for b in range(self.plan.n_buckets):
-                sharding._solve_bucket(self.batch, b, wc, chains, self.layout.n_chain, self.status)
-        finally:
-            self.batch.fused = fused
+        for b in range(self.plan.n_buckets):
+            sharding._solve_bucket(self.batch, b, wc, chains, self.layout.n_chain, self.status)
 
     def gather_only(self, group=None):
-        """The collective alone, as copy-engine pushes / NCCL (for p2p, where it is part of the solve, this is the
-        copy-engine equivalent: what a separate all-gather pass would cost)."""
+        """The collective alone (copy-engine pushes / NCCL), no solve running."""
         import torch
         from nnmnkwii_b200 import sharding
         if self.batch.peer is not None:

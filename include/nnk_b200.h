@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NNK_ABI_VERSION 3
+#define NNK_ABI_VERSION 2
 
 #define NNK_OK 0
 #define NNK_ERR_ARG -1          /* bad argument                                               */
@@ -40,7 +40,6 @@ extern "C" {
 #define NNK_F32 0
 #define NNK_F64 1
 
-#define NNK_MAX_PEERS 7 /* peer GPUs a forward solve can mirror its trajectories to (8-GPU box)          */
 #define NNK_MAX_WIN 4  /* windows per stream (static, delta, delta-delta, +1)                  */
 #define NNK_MAX_HALF 4 /* max(l, u) of any window                                              */
 #define NNK_MAX_TAPS (2 * NNK_MAX_HALF + 1)
@@ -106,14 +105,6 @@ typedef struct nnk_mlpg_args {
   const int64_t* out_off;     /* device (n_utt) first OUTPUT row of every utterance, or NULL =>
                                  utt_off (same rows in and out).  Lets a rank write its slice of
                                  a sharded batch straight into its slot of the all-gather buffer */
-  void* peer_out[NNK_MAX_PEERS]; /* nnk_mlpg_fwd only: `out` buffers of up to NNK_MAX_PEERS peer GPUs
-                                 (peer-mapped device pointers, same layout as `out`, e.g. from
-                                 nnk_peer_open).  Every trajectory value is stored to `out` AND, with
-                                 the same offset, to each peer: the all-gather of a sharded batch is
-                                 fused into the solve (SM-issued stores over NVLink) instead of being
-                                 a second pass.  NNK_ERR_UNSUPPORTED if the window set / layout falls
-                                 off the TMA-staged kernel (use nnk_peer_copy then)                */
-  int32_t n_peer;             /* 0 = no mirroring                                                */
 } nnk_mlpg_args_t;
 
 void nnk_status_decode(uint64_t status_word, nnk_status_t* out);

@@ -118,8 +118,7 @@ def _defer_check(status, device):
 
 
 def run_mlpg(mode, *, means, variances, rhs, out, offsets, lengths, order, chains, n_chain, max_T, windows_c,
-             in_ld, var_ld, go_ld, out_ld, dtype_code, go_f64, n_utt, device, check=True, out_offsets=None, status=None,
-             peers=None):
+             in_ld, var_ld, go_ld, out_ld, dtype_code, go_f64, n_utt, device, check=True, out_offsets=None, status=None):
     """Fill nnk_mlpg_args_t and enqueue nnk_mlpg_{fwd,grad,solve} on torch's current stream of
     ``device`` (the C ABI switches to the device that owns ``out`` for the launch).
     ``check``: True = synchronising status check, "deferred" = non-blocking (see poll_errors), False = none."""
@@ -136,10 +135,6 @@ def run_mlpg(mode, *, means, variances, rhs, out, offsets, lengths, order, chain
     a.utt_len = lengths.data_ptr() if lengths is not None else None
     a.order = order.data_ptr() if order is not None else None
     a.out_off = out_offsets.data_ptr() if out_offsets is not None else None
-    if peers:  # peer-mapped copies of `out` on other GPUs: the kernel mirrors every trajectory store to them
-        a.n_peer = len(peers)
-        for q, ptr in enumerate(peers):
-            a.peer_out[q] = ptr
     a.chains = chains.data_ptr()
     a.n_chain = n_chain
     a.max_T = max_T

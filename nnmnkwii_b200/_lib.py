@@ -14,9 +14,8 @@ LIB_PATH = os.environ.get("NNK_LIB_PATH") or os.path.join(_HERE, "libnnk_b200.so
 NNK_OK, NNK_ERR_ARG, NNK_ERR_UNSUPPORTED, NNK_ERR_CUDA, NNK_ERR_WORKSPACE, NNK_ERR_NOT_PD = 0, -1, -2, -3, -4, -5
 NNK_F32, NNK_F64 = 0, 1
 NNK_MAX_WIN, NNK_MAX_HALF = 4, 4
-NNK_MAX_PEERS = 7
 NNK_MAX_TAPS = 2 * NNK_MAX_HALF + 1
-ABI_VERSION = 3
+ABI_VERSION = 2
 
 
 class NnkWindows(ctypes.Structure):
@@ -56,8 +55,6 @@ class NnkMlpgArgs(ctypes.Structure):
         ("workspace_bytes", ctypes.c_size_t),
         ("status_word", ctypes.c_void_p),
         ("out_off", ctypes.c_void_p),
-        ("peer_out", ctypes.c_void_p * NNK_MAX_PEERS),
-        ("n_peer", ctypes.c_int32),
     ]
 
 

@@ -361,9 +361,6 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   p.utt_off = a.utt_off; p.out_off = a.out_off; p.utt_len = a.utt_len; p.order = a.order; p.chains = a.chains;
   p.n_utt = a.n_utt; p.n_chain = a.n_chain; p.n_groups = (a.n_chain + 31) / 32; p.max_T = a.max_T;
   p.ws = (double*)a.workspace; p.status = (unsigned long long*)a.status_word;
-  p.n_peer = (MODE == MODE_FWD) ? a.n_peer : 0;
-  for (int q = 0; q < NNK_MAX_PEERS; ++q)
-    p.peer_delta[q] = (q < p.n_peer) ? (int64_t)((const char*)a.peer_out[q] - (const char*)a.out) : 0;
   const size_t per_item = (size_t)a.max_T * NT * 32 * sizeof(double);
   size_t items_cap = per_item ? a.workspace_bytes / per_item : 0;
   int utt_per_launch = (int)(items_cap / (size_t)p.n_groups);
@@ -386,10 +383,6 @@ static int launch_mlpg(const nnk_mlpg_args_t& a, cudaStream_t st) {
   const bool staged = !force_direct_loads() && (a.win.nw == NW) &&
                       ((MODE == MODE_FWD && tma_geometry<TT, NS, TTB>(a.in_ld, a.var_ld, ES, NT, geom, smem_bytes)) ||
                        (GRAD && paired));
-  if (p.n_peer > 0 && !(staged && paired)) {
-    set_error("peer_out mirroring needs the TMA-staged assembler/solver kernel (window set or layout not supported)");
-    return NNK_ERR_UNSUPPORTED;
-  }
   for (int u0 = 0; u0 < a.n_utt; u0 += utt_per_launch) {
     const int nu = (a.n_utt - u0 < utt_per_launch) ? a.n_utt - u0 : utt_per_launch;
     p.urank0 = u0;
@@ -453,8 +446,6 @@ static int check_args(const nnk_mlpg_args_t* a, bool grad) {
   NNK_REQUIRE(a->vars && a->out && a->utt_off && a->chains && a->status_word, NNK_ERR_ARG, "NULL device pointer");
   NNK_REQUIRE(grad ? a->grad_out != nullptr : a->means != nullptr, NNK_ERR_ARG, "NULL input pointer");
   NNK_REQUIRE(a->workspace != nullptr, NNK_ERR_WORKSPACE, "NULL workspace");
-  NNK_REQUIRE(a->n_peer >= 0 && a->n_peer <= NNK_MAX_PEERS, NNK_ERR_ARG, "n_peer out of range");
-  for (int q = 0; q < a->n_peer; ++q) NNK_REQUIRE(a->peer_out[q] != nullptr, NNK_ERR_ARG, "NULL peer_out entry");
   return 0;
 }
 

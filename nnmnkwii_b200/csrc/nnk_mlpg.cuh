@@ -32,8 +32,6 @@ struct MlpgParams {
   const nnk_chain_t* chains;
   int n_utt, n_chain, n_groups, max_T, urank0;
   double* ws;
-  int n_peer;                           // forward only: mirror every output store to n_peer peer GPUs ...
-  int64_t peer_delta[NNK_MAX_PEERS];    // ... at byte offset peer_delta[q] from the local address
   unsigned long long* status;
   WinTab<NW, L, U> win;
 };

@@ -25,10 +25,6 @@
 #ifndef NNK_AS_PAIRS
 #define NNK_AS_PAIRS 0
 #endif
-// minimum resident CTAs per SM the register allocation must allow (A/B builds with more assembler warps)
-#ifndef NNK_AS_MINB
-#define NNK_AS_MINB 1
-#endif
 
 namespace nnk {
 
@@ -63,7 +59,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <typename Tin, int NW, int L, int U, bool STD, bool VARG, int MODE, int TT, int NA, int NSA, int ND, int TTB, int NSB>
-__global__ void __launch_bounds__(32 * (NA + 1), NNK_AS_MINB) mlpg_fwd_as_kernel(const __grid_constant__ MlpgParams<Tin, NW, L, U> p,
+__global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid_constant__ MlpgParams<Tin, NW, L, U> p,
                                                                     const AsGeom g) {
   constexpr int S = L + U;
   constexpr int NT = S + 1;
@@ -251,11 +247,7 @@ __global__ void __launch_bounds__(32 * (NA + 1), NNK_AS_MINB) mlpg_fwd_as_kernel
           fg[j] = 0.f;
 #pragma unroll
           for (int w = 0; w < NW; ++w) mraw[w] = *reinterpret_cast<const Tin*>(sm_m + row * ldb_m + colb[w]);
-          if (j >= NT - 1 && copy_lane && real) {  // pass-through column
-            st_stream(outp + (int64_t)f * p.out_ld, mraw[0]);
-            for (int q = 0; q < p.n_peer; ++q)
-              st_stream(reinterpret_cast<Tin*>(reinterpret_cast<char*>(outp + (int64_t)f * p.out_ld) + p.peer_delta[q]), mraw[0]);
-          }
+          if (j >= NT - 1 && copy_lane && real) st_stream(outp + (int64_t)f * p.out_ld, mraw[0]);  // pass-through column
         }
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
@@ -515,10 +507,6 @@ __global__ void __launch_bounds__(32 * (NA + 1), NNK_AS_MINB) mlpg_fwd_as_kernel
       emit(r, vrow);
     } else {
       st_stream_if(op, (Tin)y, solve);
-      // sharded batches: the same value goes to the same slot of every peer GPU's result buffer (NVLink
-      // stores issued here, behind the recurrence: the all-gather is part of the solve, not a second pass)
-      for (int q = 0; q < p.n_peer; ++q)
-        st_stream_if(reinterpret_cast<Tin*>(reinterpret_cast<char*>(op) + p.peer_delta[q]), (Tin)y, solve);
       op -= ostep;
     }
   };

@@ -11,14 +11,9 @@ count, and every group is split over the ranks by a longest-first greedy rule.  
 result buffer (``cap[b]`` = largest per-rank frame count of the bucket, so the dead rows are at most
 one utterance per bucket and rank -- no per-utterance padding).  The MLPG kernel writes straight into
 that slot (``nnk_mlpg_args_t.out_off``) and the all-gather of bucket ``b`` moves the contiguous region
-``[goff[b] + r * cap[b], ...)`` of every rank ``r`` to every other rank.  Three transports:
+``[goff[b] + r * cap[b], ...)`` of every rank ``r`` to every other rank.  Two transports:
 
-* ``"p2p"`` (default on GPUs): the result buffers are cudaMalloc allocations shared between the per-GPU
-  processes by CUDA IPC and the solve kernel itself stores every trajectory value to its own buffer AND to
-  the same slot of every peer's buffer (``nnk_mlpg_args_t.peer_out``: SM-issued stores over NVLink, behind
-  the recurrence).  Compute and collective are ONE kernel: there is no second pass over the result and
-  nothing to overlap; the pass ends with one tiny NCCL all-reduce ("everything has landed everywhere").
-* ``"peer"``: the result buffers are cudaMalloc allocations shared between the per-GPU
+* ``"peer"`` (default on GPUs): the result buffers are cudaMalloc allocations shared between the per-GPU
   processes by CUDA IPC; as soon as bucket ``b`` is solved every rank PUSHES its slot into its peers'
   buffers with copy-engine DMA over NVLink (``nnk_peer_copy``, one side stream per peer).  No SMs are
   involved, so the transfer really overlaps the solve of bucket ``b + 1`` (an NCCL all-gather kernel has
@@ -141,11 +136,11 @@ class PeerTransport(object):
                 self.peer_ptr[r] = out.value
             self.block = _DeviceBlock(self.local_ptr, (max(1, rows), cols), "<f4" if dtype == torch.float32 else "<f8")
             self.tensor = torch.as_tensor(self.block, device=device)
-            # one copy engine moves ~0.5 TB/s of NVLink's 0.9: with few peers every push is split over several
-            # streams (= engines); with seven peers the seven streams already run in parallel
-            self.split = max(1, 4 // max(1, self.world - 1))
-            self.streams = [[torch.cuda.Stream(device=device) for _ in range(self.split)] if r != self.rank else None
-                            for r in range(self.world)]
+            # ONE push stream, peers visited in the order rank+1, rank+2, ...: at any moment every GPU sends
+            # to one peer and receives from one peer (a rotating permutation), so no destination is written by
+            # seven sources at once.  (Seven concurrent per-peer streams measured 250 GB/s per GPU at N = 8,
+            # against 500 GB/s for a single source-destination pair.)
+            self.stream = torch.cuda.Stream(device=device)
             self.flag = torch.zeros(1, dtype=torch.int32, device=device)
         dist.barrier(group=group)
 
@@ -155,25 +150,18 @@ class PeerTransport(object):
         from . import _lib
         if n_rows == 0:
             return
-        per = -(-n_rows // self.split)
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            for c, st in enumerate(self.streams[r]):
-                a, e = min(n_rows, c * per), min(n_rows, (c + 1) * per)
-                if e <= a:
-                    continue
-                off, nbytes = (row0 + a) * self.row_bytes, (e - a) * self.row_bytes
-                st.wait_event(after_event)
-                _lib.check(_lib.lib.nnk_peer_copy(ctypes.c_void_p(self.peer_ptr[r] + off), ctypes.c_void_p(self.local_ptr + off),
-                                                  ctypes.c_size_t(nbytes), ctypes.c_void_p(st.cuda_stream)), "nnk_peer_copy")
+        off, nbytes = row0 * self.row_bytes, n_rows * self.row_bytes
+        st = self.stream
+        st.wait_event(after_event)
+        for k in range(1, self.world):
+            r = (self.rank + k) % self.world
+            _lib.check(_lib.lib.nnk_peer_copy(ctypes.c_void_p(self.peer_ptr[r] + off), ctypes.c_void_p(self.local_ptr + off),
+                                              ctypes.c_size_t(nbytes), ctypes.c_void_p(st.cuda_stream)), "nnk_peer_copy")
 
     def finish(self, stream):
         """``stream`` waits for this rank's pushes, then for every other rank's (tiny NCCL all-reduce)."""
         import torch.distributed as dist
-        for sts in self.streams:
-            for st in (sts or ()):
-                stream.wait_stream(st)
+        stream.wait_stream(self.stream)
         dist.all_reduce(self.flag, group=self.group)
 
     def close(self):
@@ -201,8 +189,7 @@ class ShardedBatch(object):
         self.means = torch.zeros((max(1, plan.rows_local), D_in), dtype=dtype, device=device)
         self.variances = torch.ones((max(1, plan.rows_local), D_in), dtype=dtype, device=device)
         self.peer = None
-        self.fused = (transport == "p2p")
-        if transport in ("peer", "p2p") and plan.world > 1:
+        if transport == "peer" and plan.world > 1:
             self.peer = PeerTransport(plan.rows_total, D_out, dtype, device, group)
             self.result = self.peer.tensor
         else:
@@ -287,8 +274,7 @@ def _solve_bucket(batch, b, windows_c, chains, n_chain, status):
                  offsets=m["utt_off"], lengths=m["utt_len"], order=None, chains=chains, n_chain=n_chain,
                  max_T=m["max_T"], windows_c=windows_c, in_ld=batch.D_in, var_ld=0 if var1d else batch.D_in, go_ld=0,
                  out_ld=batch.D_out, dtype_code=dev.torch_dtype_code(batch.dtype), go_f64=0, n_utt=m["n_utt"],
-                 device=batch.device, check=False, out_offsets=m["out_off"], status=status,
-                 peers=[p for p in batch.peer.peer_ptr if p] if (batch.peer is not None and batch.fused) else None)
+                 device=batch.device, check=False, out_offsets=m["out_off"], status=status)
 
 
 def _gather_bucket(result, plan, b, rank, group):
@@ -333,11 +319,6 @@ def solve_sharded(batch, windows, layout, group=None, comm_stream=None, status=N
                 _gather_bucket(batch.result, plan, b, rank, group)
         return None
     cur = torch.cuda.current_stream(batch.device)
-    if batch.peer is not None and batch.fused:  # the solve kernels store into every peer's buffer themselves
-        for b in range(plan.n_buckets):
-            _solve_bucket(batch, b, wc, chains, layout.n_chain, status)
-        batch.peer.finish(cur)
-        return None
     if batch.peer is not None:  # copy-engine pushes over NVLink, overlapped with the next bucket's solve
         for b in range(plan.n_buckets):
             _solve_bucket(batch, b, wc, chains, layout.n_chain, status)
@@ -376,14 +357,12 @@ def _comm_stream(device):
 
 
 def default_transport(device):
-    """"p2p" on CUDA devices unless NNK_SHARD_TRANSPORT says "peer" or "nccl"; the collective of the process
-    group otherwise."""
+    """"peer" on CUDA devices unless NNK_SHARD_TRANSPORT=nccl; the collective of the process group otherwise."""
     import os
     import torch
     if torch.device(device).type != "cuda":
         return None
-    t = os.environ.get("NNK_SHARD_TRANSPORT", "p2p")
-    return t if t in ("p2p", "peer", "nccl") else "p2p"
+    return "nccl" if os.environ.get("NNK_SHARD_TRANSPORT", "peer") == "nccl" else "peer"
 
 
 def mlpg_batch_sharded(means, variances, windows, lengths, layout=None, group=None, device=None, n_buckets=4,

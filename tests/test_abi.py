@@ -40,9 +40,7 @@ def test_struct_layouts_match_header():
         decl = decl.strip()
         if decl:
             for part in decl.split(","):
-                part = re.sub(r"\[[^\]]*\]", "", part)  # array members: the name precedes the brackets
                 names.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
-    assert int(re.search(r"#define NNK_MAX_PEERS (\d+)", h).group(1)) == _lib.NNK_MAX_PEERS
     assert names == [f[0] for f in _lib.NnkMlpgArgs._fields_]
 
 

@@ -20,10 +20,8 @@ def _worker(rank, world, port, lens, m, v, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from nnmnkwii_b200 import paramgen as G
     from nnmnkwii_b200.sharding import mlpg_batch_sharded
-    y = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout())  # default: p2p (stores fused into the solve)
+    y = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout())  # default transport: peer (IPC + copy engines)
     y2 = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout(), transport="nccl", n_buckets=2)
-    y4 = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout(), transport="peer", n_buckets=3)
-    assert np.array_equal(y.cpu().numpy(), y4.cpu().numpy())
     res = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout(), utterance_order=False)
     y3 = np.concatenate([res.utterance(u).cpu().numpy() for u in range(len(lens))])
     assert np.array_equal(y.cpu().numpy(), y2.cpu().numpy()) and np.array_equal(y.cpu().numpy(), y3)
