@@ -140,7 +140,9 @@ class PeerTransport(object):
             # to one peer and receives from one peer (a rotating permutation), so no destination is written by
             # seven sources at once.  (Seven concurrent per-peer streams measured 250 GB/s per GPU at N = 8,
             # against 500 GB/s for a single source-destination pair.)
-            self.stream = torch.cuda.Stream(device=device)
+            import os
+            self.n_streams = max(1, min(4, int(os.environ.get("NNK_PEER_STREAMS", "1"))))
+            self.streams = [torch.cuda.Stream(device=device) for _ in range(self.n_streams)]
             self.flag = torch.zeros(1, dtype=torch.int32, device=device)
         dist.barrier(group=group)
 
@@ -151,17 +153,19 @@ class PeerTransport(object):
         if n_rows == 0:
             return
         off, nbytes = row0 * self.row_bytes, n_rows * self.row_bytes
-        st = self.stream
-        st.wait_event(after_event)
-        for k in range(1, self.world):
+        for st in self.streams:
+            st.wait_event(after_event)
+        for k in range(1, self.world):  # stream i walks the offsets k = i+1, i+1+n, ...: n disjoint rotating permutations
             r = (self.rank + k) % self.world
+            st = self.streams[(k - 1) % self.n_streams]
             _lib.check(_lib.lib.nnk_peer_copy(ctypes.c_void_p(self.peer_ptr[r] + off), ctypes.c_void_p(self.local_ptr + off),
                                               ctypes.c_size_t(nbytes), ctypes.c_void_p(st.cuda_stream)), "nnk_peer_copy")
 
     def finish(self, stream):
         """``stream`` waits for this rank's pushes, then for every other rank's (tiny NCCL all-reduce)."""
         import torch.distributed as dist
-        stream.wait_stream(self.stream)
+        for st in self.streams:
+            stream.wait_stream(st)
         dist.all_reduce(self.flag, group=self.group)
 
     def close(self):
