@@ -795,6 +795,27 @@ def bench_extras(device, reps=5):
     out["unit_variance_mlpg_fwd_bwd"] = {"frames_per_sec": B * T / (ms * 1e-3), "ms_per_iter": ms, "batch": B, "T": T,
                                          "static_dim": sd,
                                          "includes": "autograd step: stencil fwd + loss (torch) + stencil bwd + Python/launch overhead"}
+    try:  # the same step captured once and replayed as a CUDA graph: what is left when the Python / dispatch cost is gone
+        go_s = torch.ones(B, T, sd, device=device)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                yy = AF.unit_variance_mlpg(R, mu)
+                (gg,) = torch.autograd.grad(yy, mu, go_s)
+        torch.cuda.current_stream().wait_stream(side)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        out["unit_variance_mlpg_fwd_bwd"]["ms_per_iter_cuda_graph"] = e0.elapsed_time(e1) / 20
+        out["unit_variance_mlpg_fwd_bwd"]["cuda_graph_includes"] = "fwd sweep + bwd sweep (grad_output given), one graph replay"
+    except Exception as e:
+        out["unit_variance_mlpg_fwd_bwd"]["cuda_graph_error"] = repr(e)
     # the two stencil sweeps alone (device time of the C-ABI calls, CUDA events)
     from nnmnkwii_b200 import _uvmlpg as uv
     band = uv.band_of(R, device)
