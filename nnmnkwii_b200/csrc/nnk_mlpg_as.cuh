@@ -58,6 +58,51 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- factor scratch formats --------------------------------------------------------------------------------
+// The S+1 numbers a frame needs in the backward sweep (z/d, l_1..l_S) make one scratch record per (frame, lane).
+//   float64 inputs: plain doubles, [j][lane], (S+1) * 256 B per frame and warp.
+//   float32 inputs: 48-bit records -- the upper 32 bits of the double [j][lane] followed by the next 16 bits
+//                   [j][lane] (round to nearest): 36 mantissa bits, relative error 2^-37 = 7e-12, four orders
+//                   below the float32 rounding of the result (6e-8) even at condition numbers of 1e4, and
+//                   (S+1) * 192 B per frame and warp: the scratch round trip drops from 48 to 36 B per
+//                   (frame, dim), the kernel's DRAM traffic from 76 to 64 B.  (Plain float32 records were
+//                   measured and rejected in round 1: error 7e-8 on benign data, 7e-7 on ill-conditioned.)
+template <typename Tin> struct WsFmt {  // float64: 8-byte records
+  static constexpr int REC = 256;       // bytes per (frame, j) per warp
+  static __device__ __forceinline__ void put(unsigned char* frame, int j, int lane, double v) {
+    reinterpret_cast<double*>(frame + j * 256)[lane] = v;
+  }
+  static __device__ __forceinline__ double get(const unsigned char* frame, int nt, int j, int lane) {
+    (void)nt;
+    return reinterpret_cast<const double*>(frame + j * 256)[lane];
+  }
+};
+template <> struct WsFmt<float> {       // float32 inputs: 6-byte records
+  static constexpr int REC = 192;
+  // global layout of a frame: [nt][32] uint32 (hi words) | [nt][32] uint16 (next 16 bits)
+  static __device__ __forceinline__ void put_hi_lo(unsigned char* frame, int nt, int j, int lane, double v) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v) + 0x8000ull;  // round to nearest
+    reinterpret_cast<uint32_t*>(frame)[j * 32 + lane] = (uint32_t)(bits >> 32);
+    reinterpret_cast<uint16_t*>(frame + nt * 128)[j * 32 + lane] = (uint16_t)(bits >> 16);
+  }
+  static __device__ __forceinline__ double get(const unsigned char* frame, int nt, int j, int lane) {
+    const uint32_t hi = reinterpret_cast<const uint32_t*>(frame)[j * 32 + lane];
+    const uint32_t lo = reinterpret_cast<const uint16_t*>(frame + nt * 128)[j * 32 + lane];
+    return __hiloint2double((int)hi, (int)(lo << 16));
+  }
+};
+// -DNNK_AS_WS_F64 keeps 8-byte records for float32 inputs too (A/B builds)
+#ifdef NNK_AS_WS_F64
+template <typename Tin> using WsOf = WsFmt<double>;
+#else
+template <typename Tin> using WsOf = WsFmt<Tin>;
+#endif
+template <typename Tin>
+__device__ __forceinline__ void ws_put(unsigned char* frame, int nt, int j, int lane, double v) {
+  if (WsOf<Tin>::REC == 192) WsFmt<float>::put_hi_lo(frame, nt, j, lane, v);
+  else WsFmt<double>::put(frame, j, lane, v);
+}
+
 template <typename Tin, int NW, int L, int U, bool STD, bool VARG, int MODE, int TT, int NA, int NSA, int ND, int TTB, int NSB>
 __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid_constant__ MlpgParams<Tin, NW, L, U> p,
                                                                     const AsGeom g) {
@@ -355,8 +400,9 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   }
 
   // ================================= solver warp ========================================================
-  double* const ws0 = p.ws + (size_t)item * ((size_t)p.max_T * NT * 32);
-  double* wsp = ws0 + lane;
+  constexpr int WREC = WsOf<Tin>::REC;  // scratch bytes per (frame, j) per warp
+  unsigned char* const ws0 = reinterpret_cast<unsigned char*>(p.ws) + (size_t)item * ((size_t)p.max_T * NT * 256);
+  unsigned char* wsp = ws0;  // the item's stride stays the float64 size: the workspace contract is unchanged
   double vcol[S + 1][S + 1], lcol[S + 1][S + 1], zz[S + 1];
 #pragma unroll
   for (int k = 0; k <= S; ++k) {
@@ -389,7 +435,7 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
     const double d = acc[0];
     bad = (bad == 0 && !(d > 0.0)) ? t + 1 : bad;  // linalg.pyx:79-82
     const double ivd = rcp_pos(d);
-    wsp[0] = bb * ivd;
+    ws_put<Tin>(wsp, NT, 0, lane, bb * ivd);
 #pragma unroll
     for (int k = S; k >= 2; --k) {
       zz[k] = zz[k - 1];
@@ -403,11 +449,11 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
         vcol[1][j] = acc[j];
         const double lj = acc[j] * ivd;
         lcol[1][j] = lj;
-        wsp[j * 32] = lj;
+        ws_put<Tin>(wsp, NT, j, lane, lj);
       }
       iv1 = ivd;
     }
-    wsp += NT * 32;
+    wsp += NT * WREC;
   };
 
   {
@@ -446,7 +492,7 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
   // [t0, min(T, t0 + TTB + L)) behind it (row r = t + L is emitted when x[t] becomes known)
   auto issue_ws = [&](int kb, int s) {
     const int t0 = (nbt - 1 - kb) * TTB;
-    const uint32_t nb = (uint32_t)(min(T, t0 + TTB) - t0) * NT * 32 * 8;
+    const uint32_t nb = (uint32_t)(min(T, t0 + TTB) - t0) * NT * WREC;
     uint32_t nb2 = 0;
     uint64_t b0 = 0;
     if (GRAD && !VARG) {
@@ -456,7 +502,7 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
       nb2 = (uint32_t)(((B0 + (uint64_t)((r_hi - t0 - 1) * (int64_t)ldb_v) + span_b + 15) & ~(uint64_t)15) - b0);
     }
     mbar_expect_tx(ws_full + s, nb + nb2);
-    bulk_g2s(ring + (size_t)s * g.sb_bw, ws0 + (size_t)t0 * (NT * 32), nb, ws_full + s);
+    bulk_g2s(ring + (size_t)s * g.sb_bw, ws0 + (size_t)t0 * (NT * WREC), nb, ws_full + s);
     if (GRAD && !VARG) bulk_g2s(ring + (size_t)s * g.sb_bw + g.sb_ws, reinterpret_cast<const void*>(b0), nb2, ws_full + s);
   };
   if (lane == 0)
@@ -495,13 +541,13 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
     }
     og -= ostep;
   };
-  auto back = [&](const double* fr, const unsigned char* vrow, int r) {
+  auto back = [&](const unsigned char* fr, const unsigned char* vrow, int r) {
 #pragma unroll
     for (int j = S; j > 0; --j) yw[j] = yw[j - 1];
     // oldest terms first: only the last FMA (with y[t+1]) sits on the loop-carried chain
-    double y = fr[0];
+    double y = WsOf<Tin>::get(fr, NT, 0, lane);
 #pragma unroll
-    for (int j = S; j >= 1; --j) y = fma(-fr[j * 32], yw[j], y);
+    for (int j = S; j >= 1; --j) y = fma(-WsOf<Tin>::get(fr, NT, j, lane), yw[j], y);
     yw[0] = y;
     if (GRAD) {
       emit(r, vrow);
@@ -519,17 +565,17 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
       AS_TICK(c1);
       AS_ACC(2, c0, c1);
       const int t0 = (nbt - 1 - kb) * TTB;
-      const double* smw = reinterpret_cast<const double*>(ring + (size_t)s * g.sb_bw) + lane;
+      const unsigned char* smw = ring + (size_t)s * g.sb_bw;
       // staged variance row of frame r sits at (r - t0) * ldb_v behind the factor tile
       const unsigned char* smv = ring + (size_t)s * g.sb_bw + g.sb_ws +
                                  (uint32_t)((g_v + (uint64_t)((int64_t)t0 * ldb_v)) & 15);
       if (t0 + TTB + (GRAD ? L : 0) <= T) {
 #pragma unroll
-        for (int j = TTB - 1; j >= 0; --j) back(smw + j * (NT * 32), smv + (j + L) * ldb_v, t0 + j + L);
+        for (int j = TTB - 1; j >= 0; --j) back(smw + j * (NT * WREC), smv + (j + L) * ldb_v, t0 + j + L);
       } else {
         for (int t = T - 1; t >= t0; --t) {
           const int r = t + L;
-          back(smw + (t - t0) * (NT * 32), smv + (r < T ? r - t0 : 0) * ldb_v, r);
+          back(smw + (t - t0) * (NT * WREC), smv + (r < T ? r - t0 : 0) * ldb_v, r);
         }
       }
       if (GRAD && kb == nbt - 1) {
