@@ -348,36 +348,53 @@ __global__ void __launch_bounds__(FD_BLOCK) fastdtw_kernel(const DtwParams p) {
     const int ndiag = Tx + Ty - 1;
     if (warp == 0 && fast_d) {
       // ---- (D) wavefront, one lane per active row -------------------------------------------------
+      // Every lane follows ONE row at a time: the row congruent to its lane index inside the 32-row band
+      // [imin, imin + 32) (the band of rows that are, or are about to become, active).  The row's window
+      // (lo, hi, offset) and its predecessor's window are cached in registers and reloaded only when the band
+      // has moved past the row (every ~64 diagonals), so the per-diagonal step touches shared memory only
+      // for the prefetched cost, the back-pointer and the two band-edge tests -- which are cached as well
+      // (n_in = diagonal at which row imax + 1 enters, n_out = diagonal at which row imin leaves).
       int imin = 0, imax = -1;
-      int r_lo = 0, r_hi = 0, r_off = 0, p_lo = 0, p_hi = 0;  // my row's window / offset, previous row's window
+      int n_in = (Tx > 0) ? lo[0] : INT_MAX;          // row 0 enters at diagonal 0 + lo[0]
+      int n_out = (Tx > 0) ? hi[0] : INT_MAX;         // row imin leaves at diagonal imin + hi[imin]
       int my_row = -1;
+      int r_lo = 0, r_hi = 0, r_off = 0, p_lo = 0, p_hi = 0;  // my row's window / offset, previous row's window
       double D1 = CUDART_INF, D2 = CUDART_INF;                  // my row on diagonals k-1, k-2
-      auto prefetch = [&](int kk, int base_row) {  // costs of diagonal kk for rows base_row .. base_row+31
-        const int r = base_row + lane;
-        if (kk < ndiag && r < Tx) {
-          const int jj = kk - r;
-          const int l = lo[r], h = hi[r];
-          if (jj >= l && jj < h) cp_async8(cring + (size_t)(kk % (FD_PD + 1)) * 32 + (r & 31), cbuf + off[r] + (jj - l));
-        }
+      bool fresh = false;
+      auto follow = [&](int base) {  // (re)load the cached row of this lane for the band starting at `base`
+        const int r = base + ((lane - base) & 31);
+        if (r != my_row) {
+          my_row = r;
+          if (r < Tx) {
+            r_lo = lo[r]; r_hi = hi[r]; r_off = off[r];
+            p_lo = r > 0 ? lo[r - 1] : 0; p_hi = r > 0 ? hi[r - 1] : 0;
+          } else {
+            r_lo = 0; r_hi = 0; r_off = 0; p_lo = 0; p_hi = 0;  // beyond the last row: empty window
+          }
+          fresh = true;  // D1 / D2 still hold the OLD row's last two diagonals: the neighbouring lane reads them
+        }                //   for two more steps, so they are only reset when the new row becomes active
+      };
+      auto prefetch = [&](int kk) {  // cost of this lane's cached row on diagonal kk -> ring slot of that diagonal
+        const int jj = kk - my_row;
+        if (kk < ndiag && jj >= r_lo && jj < r_hi)
+          cp_async8(cring + (size_t)(kk % (FD_PD + 1)) * 32 + lane, cbuf + r_off + (jj - r_lo));
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      for (int kk = 0; kk < FD_PD; ++kk) prefetch(kk, 0);
+      follow(0);
+      for (int kk = 0; kk < FD_PD; ++kk) prefetch(kk);
       double dist_last = 0.0;
       for (int k = 0; k < ndiag; ++k) {
-        while (imax + 1 < Tx && imax + 1 + lo[imax + 1] <= k) ++imax;
-        while (imin < Tx && imin + hi[imin] <= k) ++imin;
-        prefetch(k + FD_PD, imin);
+        while (n_in <= k) { ++imax; n_in = (imax + 1 < Tx) ? imax + 1 + lo[imax + 1] : INT_MAX; }
+        while (n_out <= k) { ++imin; n_out = (imin < Tx) ? imin + hi[imin] : INT_MAX; }
+        // a row that has left the band has no cell on any later diagonal: its lane moves on to row + 32.
+        // (Its prefetches for diagonals k .. k + FD_PD - 1 found an empty window and copied nothing.)
+        follow(imin);
+        prefetch(k + FD_PD);
         asm volatile("cp.async.wait_group %0;" ::"n"(FD_PD) : "memory");
         __syncwarp();
-        // which row does this lane hold on diagonal k?
-        int i = imin + ((lane - imin) & 31);  // the row in [imin, imin+32) congruent to lane
-        const bool active = i <= imax;
-        if (active && i != my_row) {  // row enters: cache its window (and the previous row's)
-          my_row = i;
-          r_lo = lo[i]; r_hi = hi[i]; r_off = off[i];
-          p_lo = i > 0 ? lo[i - 1] : 0; p_hi = i > 0 ? hi[i - 1] : 0;
-          D1 = CUDART_INF; D2 = CUDART_INF;
-        }
+        const int i = my_row;
+        const bool active = i <= imax && i < Tx;
+        if (active && fresh) { D1 = CUDART_INF; D2 = CUDART_INF; fresh = false; }  // the row enters
         const double upv = __shfl_sync(0xffffffffu, D1, (lane + 31) & 31);
         const double dgv = __shfl_sync(0xffffffffu, D2, (lane + 31) & 31);
         double newD = CUDART_INF;
@@ -445,21 +462,32 @@ __global__ void __launch_bounds__(FD_BLOCK) fastdtw_kernel(const DtwParams p) {
       bool ok = true;
       int32_t* pi = p.path_i + (size_t)pair * p.path_ld;
       int32_t* pj = p.path_j + (size_t)pair * p.path_ld;
+      // the window of the current row and of the row above live in registers (the row above is fetched when
+      // the path moves up, one row before it is needed), the per-row column extent of the path is
+      // accumulated in registers and stored once per row: one dependent shared-memory load per step
+      int clo = lo[i], chi = hi[i], coff = off[i];
+      int plo = i > 0 ? lo[i - 1] : 0, phi = i > 0 ? hi[i - 1] : 0, poff = i > 0 ? off[i - 1] : 0;
+      int cmin = j, cmax = j;
       while (i >= 0 && j >= 0) {
-        if (j < lo[i] || j >= hi[i]) { ok = false; break; }
+        if (j < clo || j >= chi) { ok = false; break; }
         if (lev == 0) {
           if (n >= p.path_ld) { ok = false; break; }
           pi[n] = i; pj[n] = j;
         } else {
-          jmn[i] = min(jmn[i], j);
-          jmx[i] = max(jmx[i], j);
+          cmin = min(cmin, j);
+          cmax = max(cmax, j);
         }
         ++n;
-        const unsigned char dir = bp[(size_t)(off[i] + j - lo[i])];
-        if (dir == 0) --i;
-        else if (dir == 1) --j;
-        else { --i; --j; }
+        const unsigned char dir = bp[(size_t)(coff + j - clo)];
+        if (dir != 0) --j;
+        if (dir != 1) {  // the path leaves row i
+          if (lev != 0) { jmn[i] = min(jmn[i], cmin); jmx[i] = max(jmx[i], cmax); cmin = j; cmax = j; }
+          --i;
+          clo = plo; chi = phi; coff = poff;
+          if (i > 0) { plo = lo[i - 1]; phi = hi[i - 1]; poff = off[i - 1]; }
+        }
       }
+      if (lev != 0 && ok && i >= 0) { jmn[i] = min(jmn[i], cmin); jmx[i] = max(jmx[i], cmax); }  // path ended by j < 0
       s_n = ok ? n : -1;
     }
     __syncthreads();
