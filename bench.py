@@ -543,11 +543,13 @@ def run_ours(args):
     d_chains = dev.chains_on_device(layout.chains, device)
     max_T = int(lens.max())
 
-    def step():
+    d_status = torch.zeros(1, dtype=torch.int64, device=device)  # caller-owned status word: keeps the first failure
+
+    def step():  # one launch of the solve kernel and nothing else (scratch comes from the caching allocator)
         return dev.run_mlpg("fwd", means=d_m, variances=d_v, rhs=None, out=d_out, offsets=d_off, lengths=None,
                             order=d_order, chains=d_chains, n_chain=layout.n_chain, max_T=max_T, windows_c=wc,
                             in_ld=D_IN, var_ld=D_IN, go_ld=0, out_ld=D_OUT, dtype_code=_lib.NNK_F32, go_f64=0,
-                            n_utt=N_UTT, device=device, check=False)
+                            n_utt=N_UTT, device=device, check=False, status=d_status)
 
     for _ in range(max(3, args.warmup)):
         status = step()

@@ -777,6 +777,11 @@ constexpr int DTW_NWARP = DTW_FR / 32;
 constexpr int DTW_CW = 128;    // columns per boundary ring
 constexpr int DTW_NBR = DTW_NWARP + 1;  // boundary rings (one per group in flight + the one being read)
 constexpr int DTW_POLL = 8;    // steps between progress checks / publications
+#ifndef NNK_DTW_TRIP
+#define NNK_DTW_TRIP 2
+#endif
+constexpr int DTW_TRIP = NNK_DTW_TRIP;  // columns per loop trip (cost evaluations in flight per lane)
+static_assert(DTW_POLL % DTW_TRIP == 0, "progress checks fall on trip boundaries");
 
 struct DtwFusedParams {
   const void* X;
@@ -841,7 +846,7 @@ __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedPara
     double uprev = CUDART_INF;   // D[i-1][j-1] (diagonal) = what the neighbour held one step earlier
     uint32_t bpw = 0;
     uint32_t* bprow = bp + (size_t)i * p.wpr;
-    for (int s0 = 0; s0 < nsteps; s0 += 2) {
+    for (int s0 = 0; s0 < nsteps; s0 += DTW_TRIP) {
       if ((s0 & (DTW_POLL - 1)) == 0) {
         // (1) publish: lane 0 has consumed boundary columns < s0; lane 31 has produced columns <= s0 - 32
         __syncwarp();
@@ -861,9 +866,9 @@ __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedPara
         __syncwarp();
       }
       // ---- local costs of this lane's cells of steps s0, s0 + 1 (branch-free, columns clamped) ----
-      double cst[2];
+      double cst[DTW_TRIP];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < DTW_TRIP; ++q) {
         const int jc = min(max(s0 + q - lane, 0), Ty - 1);
         const double* yr = Ys + (size_t)jc * DP;
         double r8[8];
@@ -887,7 +892,7 @@ __global__ void __launch_bounds__(DTW_FR, 1) dtw_fused_kernel(const DtwFusedPara
       }
       // ---- two relaxation steps ----
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < DTW_TRIP; ++q) {
         const int s = s0 + q;
         const int j = s - lane;
         // up = D[i-1][j]: the neighbouring lane finished that cell in the previous step

@@ -236,7 +236,10 @@ __global__ void __launch_bounds__(32 * (NA + 1)) mlpg_fwd_as_kernel(const __grid
       bulk_g2s(ring + (size_t)s * 2 * g.sb_in, reinterpret_cast<const void*>(a0), nb, my_full + s);
       if (!VARG) bulk_g2s(ring + (size_t)s * 2 * g.sb_in + g.sb_in, reinterpret_cast<const void*>(b0), nb2, my_full + s);
     };
-    constexpr int PFD = 2;  // L2 prefetch distance in turns of this warp beyond its staged tiles
+#ifndef NNK_AS_PFD
+#define NNK_AS_PFD 2
+#endif
+    constexpr int PFD = NNK_AS_PFD;  // L2 prefetch distance in turns of this warp beyond its staged tiles
     const int k_first = PAIRS ? 2 * role : role;
     if (lane == 0) {
       int k = k_first;

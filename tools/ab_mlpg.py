@@ -55,11 +55,14 @@ print("ABRES " + json.dumps(res))
 
 
 def main():
-    for lib in sys.argv[1:]:
+    run_tests = "--no-tests" not in sys.argv
+    for lib in [a for a in sys.argv[1:] if not a.startswith("--")]:
         env = dict(os.environ, NNK_LIB_PATH=os.path.abspath(lib))
         r = subprocess.run([sys.executable, "-c", INNER], env=env, capture_output=True, text=True, timeout=600)
         line = [l for l in r.stdout.splitlines() if l.startswith("ABRES ")]
         print(os.path.basename(lib), line[0][6:] if line else ("FAILED: " + r.stderr[-800:]))
+        if not run_tests:
+            continue
         t = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_mlpg_gpu.py"), "-q", "-x"], env=env,
                            capture_output=True, text=True, timeout=900)
         print(os.path.basename(lib), "pytest:", t.stdout.strip().splitlines()[-1] if t.stdout.strip() else t.stderr[-300:])
