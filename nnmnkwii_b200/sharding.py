@@ -105,6 +105,10 @@ class _DeviceBlock(object):
                                          "strides": None}
 
 
+class PeerUnavailable(RuntimeError):
+    """Raised on EVERY rank when the IPC-shared result blocks cannot be set up on some rank."""
+
+
 class PeerTransport(object):
     """Result buffer of one rank as an IPC-shared cudaMalloc block plus the mapped pointers of every
     peer's block (see module docstring).  Collective constructor: every rank of ``group`` must call it."""
@@ -118,29 +122,52 @@ class PeerTransport(object):
         self.group, self.device = group, device
         self.row_bytes = cols * (4 if dtype == torch.float32 else 8)
         nbytes = max(1, rows) * self.row_bytes
+        # Collective set-up that cannot leave some ranks inside a collective and others in an exception:
+        # every step is attempted locally, the outcome is agreed on by an all-reduce, and on any failure
+        # (CUDA IPC unavailable in this environment, peer access refused ...) EVERY rank raises PeerUnavailable,
+        # which ShardedBatch turns into the NCCL transport.
+        self.local_ptr, self.peer_ptr, self.tensor = None, [None] * self.world, None
         with torch.cuda.device(device):
-            ptr = ctypes.c_void_p()
-            _lib.check(_lib.lib.nnk_peer_alloc(ctypes.c_size_t(nbytes), ctypes.byref(ptr)), "nnk_peer_alloc")
-            self.local_ptr = ptr.value
+            import os
+            err = None
             handle = (ctypes.c_ubyte * 64)()
-            _lib.check(_lib.lib.nnk_peer_export(ctypes.c_void_p(self.local_ptr), handle), "nnk_peer_export")
+            try:
+                if os.environ.get("NNK_PEER_FORCE_FAIL") == "alloc":
+                    raise RuntimeError("forced failure (test)")
+                ptr = ctypes.c_void_p()
+                _lib.check(_lib.lib.nnk_peer_alloc(ctypes.c_size_t(nbytes), ctypes.byref(ptr)), "nnk_peer_alloc")
+                self.local_ptr = ptr.value
+                _lib.check(_lib.lib.nnk_peer_export(ctypes.c_void_p(self.local_ptr), handle), "nnk_peer_export")
+            except Exception as e:  # noqa: BLE001 -- any local failure is reported to the group below
+                err = e
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=group)
-            self.peer_ptr = [None] * self.world
-            for r in range(self.world):
-                if r == self.rank:
-                    continue
-                buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
-                out = ctypes.c_void_p()
-                _lib.check(_lib.lib.nnk_peer_open(buf, ctypes.byref(out)), "nnk_peer_open")
-                self.peer_ptr[r] = out.value
+            dist.all_gather_object(handles, None if err is not None else bytes(handle), group=group)
+            if err is None and all(h is not None for h in handles):
+                try:
+                    if os.environ.get("NNK_PEER_FORCE_FAIL") == "open" and self.rank == self.world - 1:
+                        raise RuntimeError("forced failure (test)")
+                    for r in range(self.world):
+                        if r == self.rank:
+                            continue
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                        out = ctypes.c_void_p()
+                        _lib.check(_lib.lib.nnk_peer_open(buf, ctypes.byref(out)), "nnk_peer_open")
+                        self.peer_ptr[r] = out.value
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            elif err is None:
+                err = RuntimeError("a peer could not export its result block")
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.close()
+                raise PeerUnavailable("peer-memory transport unavailable (%s)" % (err if err is not None else "failure on another rank"))
             self.block = _DeviceBlock(self.local_ptr, (max(1, rows), cols), "<f4" if dtype == torch.float32 else "<f8")
             self.tensor = torch.as_tensor(self.block, device=device)
             # ONE push stream, peers visited in the order rank+1, rank+2, ...: at any moment every GPU sends
             # to one peer and receives from one peer (a rotating permutation), so no destination is written by
             # seven sources at once.  (Seven concurrent per-peer streams measured 250 GB/s per GPU at N = 8,
             # against 500 GB/s for a single source-destination pair.)
-            import os
             self.n_streams = max(1, min(4, int(os.environ.get("NNK_PEER_STREAMS", "1"))))
             self.streams = [torch.cuda.Stream(device=device) for _ in range(self.n_streams)]
             self.flag = torch.zeros(1, dtype=torch.int32, device=device)
@@ -168,12 +195,18 @@ class PeerTransport(object):
             stream.wait_stream(st)
         dist.all_reduce(self.flag, group=self.group)
 
-    def close(self):
+    def close(self, collective=True):
+        """Unmap the peers' blocks, then (after a barrier: nobody may still map a block that is about to be
+        freed) release the own block.  Collective unless ``collective=False``."""
+        import torch.distributed as dist
+
         from . import _lib
         for r, pp in enumerate(self.peer_ptr):
             if pp:
                 _lib.lib.nnk_peer_close(ctypes.c_void_p(pp))
         self.peer_ptr = [None] * self.world
+        if collective and dist.is_initialized():
+            dist.barrier(group=self.group)
         if self.local_ptr:
             self.tensor = None
             _lib.lib.nnk_peer_free(ctypes.c_void_p(self.local_ptr))
@@ -194,7 +227,13 @@ class ShardedBatch(object):
         self.variances = torch.ones((max(1, plan.rows_local), D_in), dtype=dtype, device=device)
         self.peer = None
         if transport == "peer" and plan.world > 1:
-            self.peer = PeerTransport(plan.rows_total, D_out, dtype, device, group)
+            try:
+                self.peer = PeerTransport(plan.rows_total, D_out, dtype, device, group)
+            except PeerUnavailable as e:  # agreed on by all ranks: everybody takes the NCCL all-gather instead
+                if self.rank == 0:
+                    import sys
+                    sys.stderr.write("nnmnkwii_b200.sharding: %s; falling back to the NCCL all-gather\n" % e)
+        if self.peer is not None:
             self.result = self.peer.tensor
         else:
             self.result = torch.zeros((max(1, plan.rows_total), D_out), dtype=dtype, device=device)

@@ -25,6 +25,12 @@ def _worker(rank, world, port, lens, m, v, ret):
     res = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout(), utterance_order=False)
     y3 = np.concatenate([res.utterance(u).cpu().numpy() for u in range(len(lens))])
     assert np.array_equal(y.cpu().numpy(), y2.cpu().numpy()) and np.array_equal(y.cpu().numpy(), y3)
+    # peer set-up failing on ONE rank (simulated): every rank agrees to fall back to the NCCL all-gather
+    for mode in ("open", "alloc"):
+        os.environ["NNK_PEER_FORCE_FAIL"] = mode
+        y5 = mlpg_batch_sharded(m, v, windows_set()[2], lens, layout=G.merlin_layout(), transport="peer")
+        assert np.array_equal(y.cpu().numpy(), y5.cpu().numpy())
+    os.environ.pop("NNK_PEER_FORCE_FAIL")
     ret[rank] = y.cpu().numpy()
     dist.barrier()
     dist.destroy_process_group()
