@@ -73,3 +73,43 @@ def test_dist_callables_are_recognised_by_what_they_compute():
     for bad in (lambda x, y: float(np.abs(x - y).sum()), lambda x, y: norm(x - y) ** 2, lambda x: 0.0, 3.0):
         with pytest.raises(NotImplementedError):
             _cost_kind(bad)
+
+
+def test_uv_window_stencils_are_recovered_from_R_alone():
+    """Host side of the factored UnitVarianceMLPG sweep: from the band row of the reference's R
+    (oracle restatement of paramgen.unit_variance_mlpg_matrix, _mlpg.py:346-373) the least-squares fit
+    returns the window stencils themselves; taps that are not `h_0 * c_w` are rejected."""
+    from conftest import windows_set
+    from nnmnkwii_b200 import _uvmlpg as uv
+    ws = windows_set()[2]
+    T, nw = 200, 3
+    R = oracle.unit_variance_mlpg_matrix(ws, T).astype(np.float32)
+    peak = float(np.abs(R).max())
+    K = 23
+    mid = T // 2
+    taps = np.stack([R[mid, w * T + mid - K: w * T + mid + K + 1] for w in range(nw)])   # forward band row
+    tapsT = np.stack([R[mid - K: mid + K + 1, w * T + mid] for w in range(nw)])          # transposed band row
+    for t, want in ((taps, [[0, 1, 0], [0.5, 0, -0.5], [1, -2, 1]]), (tapsT, [[0, 1, 0], [-0.5, 0, 0.5], [1, -2, 1]])):
+        fit = uv._factor_taps(t, K, peak)
+        assert fit is not None and fit[0] == 1
+        assert np.allclose(fit[2], want, atol=2e-6)
+        assert np.array_equal(fit[1], t[0])
+    rng = np.random.default_rng(0)
+    assert uv._factor_taps(rng.standard_normal((3, 2 * K + 1)).astype(np.float32), K, 1.0) is None
+    assert uv._factor_taps(taps[:1], K, peak) is None  # a single window has nothing to factor
+
+
+def test_bench_multi_gpu_workload_helpers():
+    import bench
+    lens = bench.cfg5_lengths()
+    assert len(lens) == 8192 and lens.min() >= 200 and lens.max() <= 2000 and np.array_equal(lens, bench.cfg5_lengths())
+    assert 8.9e6 < lens.sum() < 9.1e6  # BASELINE.json configs[4]: ~9.0e6 frames
+    assert [bench.cfg5_buckets(n) for n in (1, 2, 4, 8)] == [8, 8, 4, 2]
+    m, v = bench.cfg5_utterance(17, 33)
+    m2, v2 = bench.cfg5_utterance(17, 33)
+    assert m.shape == (33, 187) and bool((m == m2).all()) and float(v.min()) >= 0.1
+    traffic, src = bench.profile_traffic(bench.DOMINANT_PROFILES)
+    assert traffic is not None and 2.0e8 < traffic < 1.0e9 and "profiles/r02_mlpg_dominant_cfg2" in src
+    assert bench.profile_traffic(["no_such_profile_*.txt"])[0] is None
+    cfg = bench.config_cfg5(8)
+    assert "configs[4]" in cfg["workload"] and cfg["buckets"] == 2 and "model" not in cfg
