@@ -99,3 +99,17 @@ def test_two_rank_gloo_matches_single_process():
     for r in (0, 1):
         assert np.array_equal(ret[r][0], ref) and np.array_equal(ret[r][1], ref)
     _ = pytest
+
+
+def test_plan_handles_fewer_utterances_than_ranks_and_empty_utterances():
+    from nnmnkwii_b200.sharding import ShardPlan
+    for lens, world in (([5, 0, 3], 8), ([7], 4), ([0, 0], 2), ([], 2), ([4, 4, 4, 4, 4], 2)):
+        lens = np.asarray(lens, dtype=np.int64)
+        plan = ShardPlan(lens, world, n_buckets=4)
+        members = [u for mem in plan.members for ids in mem for u in ids]
+        assert sorted(members) == list(range(len(lens)))
+        assert plan.rows_total >= int(lens.sum()) and plan.rows_local * world >= plan.rows_total - 0
+        assert sum(plan.frames_of_rank(r) for r in range(world)) == int(lens.sum())
+        # rows of different utterances never overlap
+        spans = sorted((int(plan.row_start[u]), int(plan.row_start[u] + lens[u])) for u in range(len(lens)) if lens[u] > 0)
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
