@@ -217,7 +217,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
         "warmup": warm, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
-        "scaling": "strong" if workload == "cfg5" else "weak",
+        "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_cfg5(args.gpus) if workload == "cfg5" else config(args.gpus),
         "cpu_baseline": base,
